@@ -1,0 +1,117 @@
+/* msvit.h -- C ABI of the B200 (sm_100a) token-grouping hot path.
+ *
+ * Drop-in boundary for the clustering plugin layer of JophiArcana/multi-state-ViT.
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference checkout).  The reference reaches this arithmetic through third-party
+ * Python packages (ncut-pytorch==1.7.9, cuml~=24.10, fast_pytorch_kmeans); a maintainer
+ * binds this library with ctypes behind ClusteringModule.forward.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless stated otherwise;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated, freed
+ *     or cached by the library, there is no global state, calls are re-entrant;
+ *   - all work is enqueued on `stream` (a cudaStream_t) of the current device and no entry
+ *     point synchronises with the host;
+ *   - return value: 0 = ok, < 0 = argument check failed (MSVIT_ERR_*), > 0 = cudaError_t;
+ *   - "segment" = one (image, parent cluster) group of tokens: rows seg_off[s] .. seg_off[s+1]-1
+ *     of the flattened token matrix.  seg_off == NULL means S equal segments of N rows.
+ *   - affinity storage: segment s is an n_s x lda_s row-major block, lda_s = (n_s + 3) & ~3, starting at
+ *     element a_off[s] (a multiple of 4).  a_off == NULL means a_off[s] = s * N * ((N + 3) & ~3).
+ */
+#ifndef MSVIT_H_
+#define MSVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSVIT_OK 0
+#define MSVIT_ERR_NULL (-1)        /* a required pointer is NULL */
+#define MSVIT_ERR_SHAPE (-2)       /* a size is out of the supported range */
+#define MSVIT_ERR_ALIGN (-3)       /* pointer / row stride alignment requirement not met */
+#define MSVIT_ERR_MODE (-4)        /* unknown dtype / distance mode */
+#define MSVIT_ERR_WORKSPACE (-5)   /* workspace too small */
+#define MSVIT_ERR_DRIVER (-6)      /* CUDA driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+#define MSVIT_F32 0
+#define MSVIT_BF16 1
+
+#define MSVIT_DIST_RBF 0       /* d = 1/2 |xi-xj|^2 / scale       sandbox/ncut_euclidean.py:19,23-29 */
+#define MSVIT_DIST_COSINE 1    /* d = 1 - cos(xi,xj)              model/clustering/modeling_spectral.py:62-69 */
+#define MSVIT_DIST_NORMPROD 2  /* d = (|xi||xj| - xi.xj) / scale  sandbox/test.py:108-110 */
+
+#define MSVIT_MAX_EIG_BLOCK 32 /* subspace block (ncut_dim + oversampling) upper bound */
+
+typedef void* msvit_stream_t; /* cudaStream_t */
+
+int msvit_version(void);
+const char* msvit_error_string(int code);
+
+/* Pairwise affinity + NCut degree.
+ * Replaces the affinity stage inside NCUT.fit_transform (call sites
+ * model/clustering/modeling_spectral.py:86,109,185,255; closed form sandbox/test.py:108-114):
+ *   A_ij = exp(-d_ij / gamma),  deg_i = sum_j A_ij,   per segment.
+ * x        [total_rows, D] row-major, MSVIT_F32 (tensor cores read it as TF32) or MSVIT_BF16.
+ *          Row stride D*elsize must be a multiple of 16 bytes, x 16-byte aligned.
+ * A        affinity blocks (layout above), may be NULL (only deg is produced).
+ * deg      [total_rows]
+ * N        max segment length (every n_s <= N). */
+int msvit_affinity_degree(const void* x, int x_dtype, float* A, float* deg, int64_t total_rows, int S, int N, int D,
+                          int mode, float gamma, float scale, const int32_t* seg_off, const int64_t* a_off,
+                          msvit_stream_t stream);
+
+/* Top-k eigenpairs of the normalised affinity D^-1/2 A D^-1/2 per segment.
+ * Replaces the eigensolve inside NCUT.fit_transform (default torch.svd_lowrank there;
+ * exact closed form sandbox/test.py:114-118).  Block subspace iteration with Rayleigh-Ritz,
+ * eigenvalues descending, eigenvector sign canonical (largest-|entry| positive, ties -> lowest row).
+ * V        [total_rows, k] (row i = embedding of token i inside its segment)
+ * lam      [S, k]
+ * iters    [S] iterations used (may be NULL)
+ * block    subspace width m, k <= m <= MSVIT_MAX_EIG_BLOCK, m % 4 == 0
+ * tol      residual tolerance |A v - lam v| <= tol for the k wanted pairs. */
+int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32_t* iters, int64_t total_rows, int S,
+                   int N, int k, int block, int max_iter, float tol, const int32_t* seg_off, const int64_t* a_off,
+                   msvit_stream_t stream);
+
+/* Lloyd k-means on the leading columns of the spectral embedding, per segment.
+ * Replaces cuml KMeans(n_clusters).fit_predict(ncut_x[:, :n_child]) (modeling_spectral.py:90), the
+ * seeded variants (:130-133, :277-278) and n_child = sum(eigenvalues > threshold) (:87,92-93).
+ * V          [total_rows, ldv] embedding, the first K_s columns are clustered
+ * lam        [S, ldv] eigenvalues, used when n_clusters <= 0:  K_s = max(1, #{lam > eig_threshold})
+ * weight     [total_rows] seeding weight (NCut degree): first centre = row argmax weight; NULL -> row 0
+ * init       [S, Kmax, Kmax] caller-supplied initial centres (row c = centre c), NULL -> farthest-point seeding
+ * labels     [total_rows] int32, canonical (first-occurrence order) ids local to the segment
+ * n_child    [S] number of non-empty clusters
+ * centres    [S, Kmax, Kmax] final centres in canonical order (may be NULL); Kmax = n_clusters>0 ? n_clusters : ldv */
+int msvit_kmeans(const float* V, const float* lam, const float* weight, const float* init, int32_t* labels,
+                 int32_t* n_child, float* centres, int64_t total_rows, int S, int N, int ldv, int n_clusters,
+                 float eig_threshold, int max_iter, const int32_t* seg_off, msvit_stream_t stream);
+
+/* Cluster-mean pooling of tokens into multi-state tokens.
+ * Replaces the per-label mean loops (modeling_spectral.py:125-127, :271-273).
+ * x [B, N, D] (MSVIT_F32 or MSVIT_BF16), labels [B, N] int64 (ids outside [0,K) are ignored)
+ * pooled [B, K, D] fp32 (empty cluster -> 0), counts [B, K] int32. */
+int msvit_pool(const void* x, int x_dtype, const int64_t* labels, float* pooled, int32_t* counts, int B, int N, int D,
+               int K, msvit_stream_t stream);
+
+/* Hierarchy bookkeeping (modeling_spectral.py:80-84,91-94; caller msvitencoder.py:491-499).
+ * msvit_build_segments: parent_indices [B, N] int64 with values in [0, P) ->
+ *   perm [B*N] int32 (flat source row of sorted row j: tokens grouped by (image, parent), stable),
+ *   seg_off [B*P + 1] int32 (segment b*P + p), a_off [B*P + 1] int64.
+ * msvit_gather_rows: xs[j, :] = x[perm[j], :]  (dtype preserved).
+ * msvit_compose_labels: child[perm[j]] = (sum of n_child of earlier parents of the image) + labels_sorted[j].
+ *   perm == NULL means identity (single parent). */
+int msvit_build_segments(const int64_t* parent_indices, int32_t* perm, int32_t* seg_off, int64_t* a_off, int B, int N,
+                         int P, msvit_stream_t stream);
+int msvit_gather_rows(const void* x, int x_dtype, const int32_t* perm, void* xs, int64_t total_rows, int D,
+                      msvit_stream_t stream);
+int msvit_compose_labels(const int32_t* labels_sorted, const int32_t* n_child, const int32_t* perm,
+                         const int32_t* seg_off, int64_t* child, int B, int N, int P, msvit_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSVIT_H_ */

@@ -1,0 +1,70 @@
+"""Synthetic ViT token tensors for tests and benchmarks.
+
+iid Gaussian tokens give a degenerate NCut spectrum (lambda ~ [1, .004, .004, ...]) whose
+eigenvectors and labels are numerically arbitrary, so every workload here is a planted
+mixture: per image, K random centres with unequal class sizes plus isotropic noise.
+Generation is on the CPU with a per-image seed so that every rank / shard can produce
+exactly its own images without communication.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+# name -> (B, N, D, K)   (BASELINE.json configs[0..3])
+CONFIGS = {
+    "C1": (8, 196, 768, 8),
+    "C2": (1024, 196, 768, 8),
+    "C3": (512, 576, 1024, 16),
+    "C4": (256, 1024, 768, 4),
+}
+
+
+def default_scale(D: int) -> float:
+    """Distance scale used by the benchmark workloads: s = D / 4 (about median |xi-xj|^2 / 10)."""
+    return D / 4.0
+
+
+def planted_image(b: int, N: int, D: int, K: int, noise: float = 0.5, seed: int = 1212) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Image `b` of a workload: (x [N, D] fp32, planted labels [N] int64)."""
+    g = torch.Generator().manual_seed(seed + b)
+    centres = torch.randn(K, D, generator=g)
+    probs = torch.arange(1, K + 1, dtype=torch.float32)
+    probs = probs / probs.sum()
+    lab = torch.multinomial(probs, N, replacement=True, generator=g)
+    x = centres[lab] + noise * torch.randn(N, D, generator=g)
+    return x, lab
+
+
+def planted_tokens(B: int, N: int, D: int, K: int, noise: float = 0.5, seed: int = 1212, first: int = 0,
+                   out: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Images first .. first+B-1 -> (x [B, N, D] fp32, labels [B, N])."""
+    x = out if out is not None else torch.empty(B, N, D)
+    lab = torch.empty(B, N, dtype=torch.long)
+    for i in range(B):
+        xi, li = planted_image(first + i, N, D, K, noise, seed)
+        x[i].copy_(xi)
+        lab[i] = li
+    return x, lab
+
+
+def planted_features(n: int, D: int, k: int, noise: float = 0.5, seed: int = 1212, first: int = 0,
+                     chunk: int = 65536) -> torch.Tensor:
+    """Rows first .. first+n-1 of the dataset-level (DeepCluster-style) workload: centres[lab] + noise."""
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn(k, D, generator=g)
+    out = torch.empty(n, D)
+    start = (first // chunk) * chunk
+    pos = 0
+    c = start
+    while pos < n:
+        gc = torch.Generator().manual_seed(seed + 1 + c // chunk)
+        lab = torch.randint(0, k, (chunk,), generator=gc)
+        blk = centres[lab] + noise * torch.randn(chunk, D, generator=gc)
+        lo = max(first, c) - c
+        hi = min(first + n, c + chunk) - c
+        out[pos:pos + hi - lo] = blk[lo:hi]
+        pos += hi - lo
+        c += chunk
+    return out
