@@ -71,10 +71,12 @@ int msvit_affinity_degree(const void* x, int x_dtype, float* A, float* deg, int6
  * lam      [S, k]
  * iters    [S] iterations used (may be NULL)
  * block    subspace width m, k <= m <= MSVIT_MAX_EIG_BLOCK, m % 4 == 0
- * tol      residual tolerance |A v - lam v| <= tol for the k wanted pairs. */
+ * tol      residual tolerance |Abar v - lam v| <= tol for the k wanted pairs
+ * lam_floor wanted pairs whose eigenvalue estimate is below lam_floor are exempt from the residual test
+ *          (they are never clustered on when the eigenvalue threshold selects the children); 0 = none. */
 int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32_t* iters, int64_t total_rows, int S,
-                   int N, int k, int block, int max_iter, float tol, const int32_t* seg_off, const int64_t* a_off,
-                   msvit_stream_t stream);
+                   int N, int k, int block, int max_iter, float tol, float lam_floor, const int32_t* seg_off,
+                   const int64_t* a_off, msvit_stream_t stream);
 
 /* Lloyd k-means on the leading columns of the spectral embedding, per segment.
  * Replaces cuml KMeans(n_clusters).fit_predict(ncut_x[:, :n_child]) (modeling_spectral.py:90), the

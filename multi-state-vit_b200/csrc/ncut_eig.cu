@@ -37,6 +37,7 @@ struct Params {
   int k, m;
   int max_iter, rr_every;
   float tol;
+  float lam_floor;  // wanted pairs whose Ritz value is below this are exempt from the residual test
   int a_resident;  // 1: the affinity block is copied into shared memory once (TMA bulk copy)
 };
 
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
           for (int c = 0; c < kk; ++c) {
             float v = 0.f;
             for (int w = 0; w < kWarps; ++w) v += scratch[w * MSVIT_MAX_EIG_BLOCK + c];
-            worst = fmaxf(worst, v);
+            if (theta[c] >= P.lam_floor) worst = fmaxf(worst, v);
           }
           misc[1] = worst;
         }
@@ -510,7 +511,7 @@ static int launch(const Params& P, int grid, size_t smem, cudaStream_t stream) {
 
 extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32_t* iters,
                               int64_t total_rows, int S, int N, int k, int block, int max_iter, float tol,
-                              const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream_) {
+                              float lam_floor, const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream_) {
   using namespace msvit;
   using namespace msvit::eig;
   if (!A || !deg || !V || !lam) return MSVIT_ERR_NULL;
@@ -526,7 +527,7 @@ extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float*
   P.A = A; P.deg = deg; P.V = V; P.lam = lam; P.iters = iters;
   P.seg_off = seg_off; P.a_off = a_off;
   P.S = S; P.N = N; P.k = k; P.m = block;
-  P.max_iter = max_iter; P.rr_every = 3; P.tol = tol;
+  P.max_iter = max_iter; P.rr_every = 3; P.tol = tol; P.lam_floor = lam_floor;
   size_t smem = static_cast<size_t>(make_layout(N, block, true).total) * 4;
   P.a_resident = smem <= kMaxSmem ? 1 : 0;
   if (!P.a_resident) smem = static_cast<size_t>(make_layout(N, block, false).total) * 4;

@@ -40,74 +40,169 @@ def default_block(k: int, oversample: int = 8) -> int:
     return max(m, (k + 3) & ~3)
 
 
+class ClusterPlan:
+    """Pre-allocated execution plan of the whole hot path for a fixed problem shape.
+
+    All buffers (affinity blocks, degree, eigenvectors, labels, pooled tokens, segment tables) are allocated
+    once; `run` only enqueues kernels on the current stream -- no allocation, no host synchronisation -- so a
+    plan can be replayed every step and captured in a CUDA graph.  The tensors in the returned ClusterOutput
+    are views of plan-owned memory and are overwritten by the next `run`.
+    """
+
+    STAGES = ("segments", "affinity", "eig", "kmeans", "compose", "pool")
+
+    def __init__(self, B: int, N: int, D: int, dtype: torch.dtype = torch.float32, device="cuda", *, ncut_dim: int,
+                 n_clusters: Optional[int] = None, eigenvalue_threshold: Optional[float] = None, mode: str = "rbf",
+                 gamma: float = 3.0, scale: Optional[float] = None, n_parents: int = 1, kmeans_iters: int = 100,
+                 eig_iters: int = 60, eig_tol: float = 2e-5, oversample: int = 8, pool_k: Optional[int] = None,
+                 want_pool: bool = True):
+        if mode not in _lib.DIST:
+            raise ValueError(f"unknown distance {mode!r}")
+        if n_clusters is None and eigenvalue_threshold is None:
+            raise ValueError("give n_clusters or eigenvalue_threshold")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("msvit.cluster_tokens runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"tokens must be float32 or bfloat16, got {dtype}")
+        self.lib = _lib.load()
+        self.B, self.N, self.D, self.P = int(B), int(N), int(D), int(n_parents)
+        self.dtype, self.device = dtype, dev
+        self.dtype_code = _lib.F32 if dtype == torch.float32 else _lib.BF16
+        self.k = int(ncut_dim)
+        self.block = default_block(self.k, oversample)
+        self.mode = _lib.DIST[mode]
+        self.gamma = float(gamma)
+        self.scale = float(D) if scale is None else float(scale)
+        self.nk = int(n_clusters) if n_clusters is not None else 0
+        self.thr = float(eigenvalue_threshold) if eigenvalue_threshold is not None else 0.0
+        # eigenpairs below half the threshold are never clustered on: exempt them from the residual test
+        self.lam_floor = 0.5 * self.thr if self.nk == 0 else 0.0
+        self.kmeans_iters, self.eig_iters, self.eig_tol = int(kmeans_iters), int(eig_iters), float(eig_tol)
+        self.want_pool = bool(want_pool)
+        self.Kp = int(pool_k) if pool_k is not None else self.P * (self.nk if self.nk > 0 else self.k)
+        B, N, D, P, k = self.B, self.N, self.D, self.P, self.k
+        self.S = B * P
+        rows = B * N
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            if P == 1:
+                self.perm = self.seg_off = self.a_off = self.xs = None
+                a_numel = rows * ops.lda_of(N)
+            else:
+                self.perm = torch.empty(rows, **i32)
+                self.seg_off = torch.empty(self.S + 1, **i32)
+                self.a_off = torch.empty(self.S + 1, dtype=torch.int64, device=dev)
+                self.xs = torch.empty(rows, D, dtype=dtype, device=dev)
+                a_numel = B * ops.affinity_stride(N)
+            self.A = torch.empty(a_numel, **f32)
+            self.deg = torch.empty(rows, **f32)
+            self.V = torch.empty(rows, k, **f32)
+            self.lam = torch.empty(self.S, k, **f32)
+            self.iters = torch.empty(self.S, **i32)
+            self.labels_sorted = torch.empty(rows, **i32)
+            self.n_child = torch.empty(self.S, **i32)
+            self.child = torch.empty(B, N, dtype=torch.int64, device=dev)
+            self.pooled = torch.empty(B, self.Kp, D, **f32) if want_pool else None
+            self.counts = torch.empty(B, self.Kp, **i32) if want_pool else None
+
+    def run(self, x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, events=None) -> "ClusterOutput":
+        """Enqueue the hot path for x [B, N, D].  `events`, if given, is a list of len(STAGES)+1 CUDA events that
+        are recorded around the stages (per-stage timing)."""
+        B, N, D, P, k, S = self.B, self.N, self.D, self.P, self.k, self.S
+        if tuple(x.shape) != (B, N, D) or x.dtype != self.dtype or x.device != self.device:
+            raise ValueError(f"plan was built for {(B, N, D)} {self.dtype} on {self.device}, "
+                             f"got {tuple(x.shape)} {x.dtype} on {x.device}")
+        if not x.is_contiguous():
+            x = x.contiguous()
+        if (parent_indices is None) != (P == 1):
+            raise ValueError("parent_indices must be given exactly when the plan has n_parents > 1")
+        lib, check, p = self.lib, _lib.check, ops._ptr
+        rows = B * N
+        st = torch.cuda.current_stream(self.device).cuda_stream
+
+        def mark(i):
+            if events is not None:
+                events[i].record()
+
+        with torch.cuda.device(self.device):
+            mark(0)
+            if P > 1:
+                if parent_indices.shape != (B, N) or parent_indices.dtype != torch.int64:
+                    raise ValueError("parent_indices must be int64 [batch, tokens]")
+                parent_indices = parent_indices.contiguous()
+                check(lib.msvit_build_segments(p(parent_indices), p(self.perm), p(self.seg_off), p(self.a_off), B, N, P,
+                                               st), "msvit_build_segments")
+                check(lib.msvit_gather_rows(p(x), self.dtype_code, p(self.perm), p(self.xs), rows, D, st),
+                      "msvit_gather_rows")
+                xs = self.xs
+            else:
+                xs = x
+            mark(1)
+            check(lib.msvit_affinity_degree(p(xs), self.dtype_code, p(self.A), p(self.deg), rows, S, N, D, self.mode,
+                                            self.gamma, self.scale, p(self.seg_off), p(self.a_off), st),
+                  "msvit_affinity_degree")
+            mark(2)
+            check(lib.msvit_ncut_eig(p(self.A), p(self.deg), p(self.V), p(self.lam), p(self.iters), rows, S, N, k,
+                                     self.block, self.eig_iters, self.eig_tol, self.lam_floor, p(self.seg_off),
+                                     p(self.a_off), st), "msvit_ncut_eig")
+            mark(3)
+            check(lib.msvit_kmeans(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted), p(self.n_child),
+                                   None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters, p(self.seg_off), st),
+                  "msvit_kmeans")
+            mark(4)
+            check(lib.msvit_compose_labels(p(self.labels_sorted), p(self.n_child), p(self.perm), p(self.seg_off),
+                                           p(self.child), B, N, P, st), "msvit_compose_labels")
+            mark(5)
+            if self.want_pool:
+                check(lib.msvit_pool(p(x), self.dtype_code, p(self.child), p(self.pooled), p(self.counts), B, N, D,
+                                     self.Kp, st), "msvit_pool")
+            mark(6)
+
+        if self.perm is not None:
+            idx = self.perm.long()
+            V_tok = torch.empty_like(self.V)
+            V_tok[idx] = self.V
+            deg_tok = torch.empty_like(self.deg)
+            deg_tok[idx] = self.deg
+        else:
+            V_tok, deg_tok = self.V, self.deg
+        aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0) else None
+        return ClusterOutput(labels=self.child, pooled=self.pooled, counts=self.counts, eigvecs=V_tok.view(B, N, k),
+                             eigvals=self.lam.view(B, P, k), n_child=self.n_child.view(B, P),
+                             degree=deg_tok.view(B, N), iters=self.iters.view(B, P), affinity=aff)
+
+
 def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, *, ncut_dim: int,
                    n_clusters: Optional[int] = None, eigenvalue_threshold: Optional[float] = None,
                    mode: str = "rbf", gamma: float = 3.0, scale: Optional[float] = None,
                    n_parents: Optional[int] = None, kmeans_iters: int = 100, eig_iters: int = 60,
                    eig_tol: float = 2e-5, oversample: int = 8, pool_k: Optional[int] = None,
                    want_pool: bool = True, keep_affinity: bool = False) -> ClusterOutput:
+    """One-shot form: builds a ClusterPlan for x's shape and runs it (buffers are owned by the result)."""
     if x.dim() != 3:
         raise ValueError("x must be [batch, tokens, hidden]")
-    if mode not in _lib.DIST:
-        raise ValueError(f"unknown distance {mode!r}")
-    if n_clusters is None and eigenvalue_threshold is None:
-        raise ValueError("give n_clusters or eigenvalue_threshold")
     if not x.is_cuda:
         raise RuntimeError("msvit.cluster_tokens runs on CUDA (sm_100a) only; there is no CPU fallback")
     B, N, D = x.shape
-    x = x.contiguous()
-    k = int(ncut_dim)
-    block = default_block(k, oversample)
-    s = float(D) if scale is None else float(scale)
-    flat = x.view(B * N, D)
-
     if parent_indices is None:
         P = 1
     else:
-        if parent_indices.shape != (B, N):
+        if tuple(parent_indices.shape) != (B, N):
             raise ValueError("parent_indices must be [batch, tokens]")
-        parent_indices = parent_indices.contiguous()
         # the reference reads this on the host too (modeling_spectral.py:80); pass n_parents to skip the sync
         P = int(n_parents) if n_parents is not None else int(parent_indices.max().item()) + 1
-
-    if P == 1:
-        perm = seg_off = a_off = None
-        xs = flat
-        S = B
-        a_numel = B * N * ops.lda_of(N)
-    else:
-        perm, seg_off, a_off = ops.build_segments(parent_indices, P)
-        xs = ops.gather_rows(flat, perm)
-        S = B * P
-        a_numel = B * ops.affinity_stride(N)
-
-    A, deg = ops.affinity_degree(xs, S, N, _lib.DIST[mode], float(gamma), s, seg_off, a_off, a_numel, True)
-    V, lam, iters = ops.ncut_eig(A, deg, S, N, k, block, int(eig_iters), float(eig_tol), seg_off, a_off)
-    nk = int(n_clusters) if n_clusters is not None else 0
-    thr = float(eigenvalue_threshold) if eigenvalue_threshold is not None else 0.0
-    labels_sorted, n_child, _ = ops.kmeans(V, lam, deg, None, S, N, nk, thr, int(kmeans_iters), seg_off)
-    child = ops.compose_labels(labels_sorted, n_child, perm, seg_off, B, N, P)
-
-    if perm is not None:
-        idx = perm.long()
-        V_tok = torch.empty_like(V)
-        V_tok[idx] = V
-        deg_tok = torch.empty_like(deg)
-        deg_tok[idx] = deg
-    else:
-        V_tok, deg_tok = V, deg
-
-    pooled = counts = None
-    if want_pool:
-        Kp = pool_k if pool_k is not None else P * (nk if nk > 0 else k)
-        pooled, counts = ops.pool(x, child, int(Kp))
-
-    aff = None
-    if keep_affinity and P == 1 and N % 4 == 0:
-        aff = A.view(B, N, N)
-    return ClusterOutput(labels=child, pooled=pooled, counts=counts, eigvecs=V_tok.view(B, N, k),
-                         eigvals=lam.view(B, P, k), n_child=n_child.view(B, P), degree=deg_tok.view(B, N),
-                         iters=iters.view(B, P), affinity=aff)
+        if P == 1:
+            parent_indices = None
+    plan = ClusterPlan(B, N, D, x.dtype, x.device, ncut_dim=ncut_dim, n_clusters=n_clusters,
+                       eigenvalue_threshold=eigenvalue_threshold, mode=mode, gamma=gamma, scale=scale, n_parents=P,
+                       kmeans_iters=kmeans_iters, eig_iters=eig_iters, eig_tol=eig_tol, oversample=oversample,
+                       pool_k=pool_k, want_pool=want_pool)
+    out = plan.run(x, parent_indices)
+    if not keep_affinity:
+        out.affinity = None
+    return out
 
 
 def affinity(x: torch.Tensor, mode: str = "rbf", gamma: float = 3.0, scale: Optional[float] = None):
@@ -120,13 +215,15 @@ def affinity(x: torch.Tensor, mode: str = "rbf", gamma: float = 3.0, scale: Opti
     return A.view(B, N, lda), deg.view(B, N)
 
 
-def ncut_eig(A: torch.Tensor, deg: torch.Tensor, k: int, *, max_iter: int = 60, tol: float = 2e-5, oversample: int = 8):
+def ncut_eig(A: torch.Tensor, deg: torch.Tensor, k: int, *, max_iter: int = 60, tol: float = 2e-5, oversample: int = 8,
+             lam_floor: float = 0.0):
     """A [B, N, lda] (as returned by `affinity`), deg [B, N] -> (V [B, N, k], lam [B, k], iters [B])."""
     B, N, lda = A.shape
     if lda != ops.lda_of(N):
         raise ValueError("A must be [B, N, (N+3)&~3]")
     V, lam, iters = ops.ncut_eig(A.contiguous().view(-1), deg.contiguous().view(-1), B, N, int(k),
-                                 default_block(int(k), oversample), int(max_iter), float(tol), None, None)
+                                 default_block(int(k), oversample), int(max_iter), float(tol), float(lam_floor),
+                                 None, None)
     return V.view(B, N, k), lam, iters
 
 

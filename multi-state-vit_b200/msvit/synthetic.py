@@ -30,9 +30,13 @@ def planted_image(b: int, N: int, D: int, K: int, noise: float = 0.5, seed: int 
     """Image `b` of a workload: (x [N, D] fp32, planted labels [N] int64)."""
     g = torch.Generator().manual_seed(seed + b)
     centres = torch.randn(K, D, generator=g)
-    probs = torch.arange(1, K + 1, dtype=torch.float32)
-    probs = probs / probs.sum()
-    lab = torch.multinomial(probs, N, replacement=True, generator=g)
+    # class sizes proportional to c + 1 (unequal sizes => distinct eigenvalues), exact rather than sampled so
+    # that no class is ever missing: a missing class would put a wanted eigenvector into the noise bulk,
+    # where eigenvectors -- and hence labels -- are numerically arbitrary for ANY solver
+    w = torch.arange(1, K + 1, dtype=torch.float64)
+    sizes = torch.floor(w / w.sum() * N).long()
+    sizes[K - 1] += N - int(sizes.sum())
+    lab = torch.repeat_interleave(torch.arange(K), sizes)[torch.randperm(N, generator=g)]
     x = centres[lab] + noise * torch.randn(N, D, generator=g)
     return x, lab
 
