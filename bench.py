@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the token-grouping hot path (BASELINE.json metric: images/sec of NCut token clustering + pooling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole hot path (affinity+degree -> top-k NCut eigenvectors -> k-means -> label
+composition -> cluster-mean pooling) over one batch of synthetic planted-mixture ViT tokens.  At N=1 the
+workload is BASELINE.json configs[1] (ViT-B/16, 196 tokens, d=768, batch 1024, k=8).  For N>1 every rank runs
+the same per-GPU batch on its own images (weak scaling, no collective on the data path); the step time is
+the max over ranks, `value` = images all ranks processed / that time.
+
+Printed JSON (rank 0, one line): the base contract keys plus
+  roofline      the dominant kernel of the step (by CUDA-event share): algorithmic bytes (or flops) per launch
+                / its average launch duration, against MEASURED_PEAKS.json
+  stages        per-stage average ms and achieved rate (same events)
+  cpu_baseline  the CPU oracle (a port: the reference's arithmetic lives in packages absent from the image)
+                timed on this box's host cores on a bounded sample of the same workload
+  e2e           same metric through the public host-buffer API (msvit.HostClusterer): pinned host tokens ->
+                H2D -> kernels -> D2H of labels / pooled tokens / counts, all inside the timed region
+`--impl reference` times the CPU oracle alone (rank 0 only) and prints the same line shape.
+
+Only the cpu_baseline leg and `--impl reference` import oracle/; the product path never does.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "multi-state-vit_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec NCut token clustering+pooling, ViT-B/16 196 tok, at 1/2/4/8 B200"
+UNIT = "images/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        p["_source"] = "measured (MEASURED_PEAKS.json)"
+        return p
+    p = dict(FALLBACK_PEAKS)
+    p["_source"] = "fallback (B200_PROFILING.md)"
+    return p
+
+
+def workload(name: str):
+    from msvit.synthetic import CONFIGS
+    B, N, D, K = CONFIGS[name]
+    k = {"C1": 8, "C2": 8, "C3": 16, "C4": 8}[name]
+    return B, N, D, K, k
+
+
+def workload_string(name, B, N, D, K, k, dtype_name):
+    return (f"{name}: ViT-B/16 224px tokens [B={B} per GPU, N={N}, D={D}] {dtype_name}, rbf NCut affinity "
+            f"(gamma=3, scale=D/4), k={k} eigenvectors, K={K} k-means clusters, cluster-mean pooling")
+
+
+# ------------------------------------------------------------------------------------------ algorithmic work
+def stage_work(B, N, D, K, k, esz):
+    """Algorithmic bytes / flops of ONE launch of each stage kernel over B images (DESIGN.md section 4;
+    per-image figures are SURVEY.md section 8d's)."""
+    lda = (N + 3) & ~3
+    w = {}
+    # affinity: read X once, write A (fp32, padded rows) and deg; flops = Gram 2 N^2 D
+    w["affinity"] = {"bytes": B * (esz * N * D + 4 * N * lda + 4 * N), "flops": 2.0 * B * N * N * D}
+    # eigensolver: read A and deg once (A is then shared-memory resident), write V and lambda
+    w["eig"] = {"bytes": B * (4 * N * lda + 4 * N + 4 * N * k + 4 * k), "flops": 0.0}
+    # k-means: read V, lambda, deg; write labels (int32) and the child count
+    w["kmeans"] = {"bytes": B * (4 * N * k + 4 * k + 4 * N + 4 * N + 4), "flops": 0.0}
+    # label composition: read int32 labels + counts, write int64 labels
+    w["compose"] = {"bytes": B * (4 * N + 4 + 8 * N), "flops": 0.0}
+    # pooling: read X and int64 labels, write pooled fp32 and counts
+    w["pool"] = {"bytes": B * (esz * N * D + 8 * N + 4 * K * D + 4 * K), "flops": 0.0}
+    return w
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 100 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(N, D, K, k, n_images: int, batch: int = 8):
+    """Times the CPU oracle (torch CPU restatement, all host threads) on `n_images` images of the workload,
+    processed in batches of `batch` (BASELINE.json configs[0] is batch 8).  Returns (images/s, cores, seconds)."""
+    from oracle import ncut_oracle as O
+    from msvit.synthetic import default_scale, planted_tokens
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pool_n = min(n_images, 64)
+    x, _ = planted_tokens(pool_n, N, D, K)
+    s = default_scale(D)
+
+    def one(b0):
+        xb = x[b0:b0 + batch]
+        child, _, _, _ = O.cluster_tokens(xb, None, ncut_dim=k, n_clusters=K, scale=s)
+        O.pool(xb, child, K)
+        return xb.shape[0]
+
+    one(0)  # warm-up
+    done = 0
+    t0 = time.perf_counter()
+    while done < n_images:
+        done += one((done % pool_n) // batch * batch if pool_n >= batch else 0)
+    dt = time.perf_counter() - t0
+    return done / dt, torch.get_num_threads(), dt, done
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path for this workload.  The reference's own arithmetic
+    (ncut-pytorch / cuML) is not installable here, so this is the oracle port, on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, N, D, K, k = workload(args.config)
+    per_step = args.ref_images_per_step
+    for _ in range(args.warmup):
+        cpu_oracle_rate(N, D, K, k, 8)
+    t_total, n_total, cores = 0.0, 0, 1
+    for _ in range(args.steps):
+        rate, cores, dt, done = cpu_oracle_rate(N, D, K, k, per_step)
+        t_total += dt
+        n_total += done
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, B, N, D, K, k, args.dtype),
+                   "sample_per_step": f"{per_step} images in batches of 8 (CPU oracle port of the reference path)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_total} images of {args.config} in batches of 8, torch CPU {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    import msvit
+    from msvit.functional import ClusterPlan, HostClusterer
+    from msvit.synthetic import default_scale, planted_tokens
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    msvit._lib.load()  # fail loudly if libmsvit.so is missing
+
+    B, N, D, K, k = workload(args.config)
+    dtype = torch.float32 if args.dtype == "float32" else torch.bfloat16
+    esz = 4 if dtype == torch.float32 else 2
+    scale = default_scale(D)
+
+    # this rank's images (weak scaling: B per GPU, image ids rank*B .. rank*B+B-1), generated on the host
+    host = torch.empty(B, N, D, dtype=dtype).pin_memory()
+    planted_tokens(B, N, D, K, first=rank * B, out=host) if dtype == torch.float32 else host.copy_(
+        planted_tokens(B, N, D, K, first=rank * B)[0])
+    x = host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    plan = ClusterPlan(B, N, D, dtype, dev, ncut_dim=k, n_clusters=K, scale=scale)
+    n_st = len(ClusterPlan.STAGES)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: K steps, per-stage events recorded inside the same region
+    for _ in range(args.warmup):
+        out = plan.run(x)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(n_st + 1)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for s in range(args.steps):
+        out = plan.run(x, events=events[s])
+    t_end.record()
+    barrier()
+    ms_total = reduce_max(t_begin.elapsed_time(t_end))
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = {name: sum(ev[i].elapsed_time(ev[i + 1]) for ev in events) / args.steps
+                for i, name in enumerate(ClusterPlan.STAGES)}
+    iters = out.iters.float()
+    eig_iters = {"mean": float(iters.mean()), "max": int(iters.max())}
+
+    # ---- end to end through the public host-buffer API
+    hc = HostClusterer(B, N, D, dtype, dev, ncut_dim=k, n_clusters=K, scale=scale, chunk=args.e2e_chunk)
+    for _ in range(max(1, min(args.warmup, 3))):
+        res = hc.run(host)
+    barrier()
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = args.e2e_steps or args.steps
+    barrier()
+    wall0 = time.perf_counter()
+    e_begin.record()
+    for s in range(e2e_steps):
+        res = hc.run(host)
+    e_end.record()
+    barrier()
+    e2e_wall = time.perf_counter() - wall0
+    e2e_ms = reduce_max(max(e_begin.elapsed_time(e_end), 1e3 * e2e_wall))
+    # the end-to-end results agree with the device-resident ones
+    if not torch.equal(res.labels, out.labels.cpu()):
+        raise RuntimeError("end-to-end labels differ from the device-resident run")
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    work = stage_work(B, N, D, K, k, esz)
+    stages = {}
+    for name in ClusterPlan.STAGES:
+        ms = stage_ms[name]
+        if name not in work or ms <= 0:
+            continue
+        w = work[name]
+        stages[name] = {"ms": round(ms, 4), "GB/s": round(w["bytes"] / ms / 1e6, 1)}
+        if w["flops"]:
+            stages[name]["TFLOP/s"] = round(w["flops"] / ms / 1e9, 1)
+    dominant = max(stages, key=lambda n: stages[n]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.config, {}).get(dominant)
+    if dominant == "affinity":
+        # the Gram contraction is the one tensor-core-bound kernel of the path
+        ach = stages[dominant]["TFLOP/s"]
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["_source"] + ", sustained bf16"}
+    else:
+        ach = stages[dominant]["GB/s"]
+        peak = peaks["hbm_gbs"]
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["_source"]}
+    roof["share_of_step"] = round(stages[dominant]["ms"] / sum(s["ms"] for s in stages.values()), 3)
+
+    cpu_rate, cores, cpu_s, cpu_n = cpu_oracle_rate(N, D, K, k, args.cpu_images)
+
+    ms_step = ms_total / args.steps
+    value = world * B / ms_step * 1e3
+    n_launch_step = sum(1 for n in ClusterPlan.STAGES if stage_ms[n] > 0 and n in work)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, B, N, D, K, k, args.dtype),
+                   "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2_policy": f"inputs larger than L2 ({B * N * D * esz / 1e6:.0f} MB tokens + "
+                                f"{B * N * ((N + 3) & ~3) * 4 / 1e6:.0f} MB affinity per step vs 126 MB L2)",
+                   "eig_iters": eig_iters},
+        "roofline": roof, "stages": stages,
+        "cpu_baseline": {"value": round(cpu_rate, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cpu_n} images of {args.config} in batches of 8 ({cpu_s:.1f} s), "
+                                   f"torch CPU oracle, {cores} threads"},
+        "e2e": {"value": round(world * B * e2e_steps / e2e_ms * 1e3, 1), "unit": UNIT,
+                "h2d_bytes_per_step": hc.h2d_bytes, "d2h_bytes_per_step": hc.d2h_bytes, "steps": e2e_steps,
+                "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "msvit.HostClusterer.run (pinned host buffers)"},
+        "gpu_launches": n_launch_step * args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--dtype", default="float32", choices=["float32", "bfloat16"],
+                    help="dtype of the token tensor handed to the path (the reference hands fp32 hidden states)")
+    ap.add_argument("--cpu-images", type=int, default=2048, help="images in the cpu_baseline sample")
+    ap.add_argument("--ref-images-per-step", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--e2e-chunk", type=int, default=128)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,7 @@ struct Params {
 struct Shared {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t conv[kMaxStages];  // fp32 input: the staged tile has been rounded to TF32 by the norm warps
   uint64_t tmem_full;
   uint64_t tmem_empty;
   uint32_t tmem_base;
@@ -61,18 +62,26 @@ struct Shared {
 };
 
 // Sum of squares of one 128-byte row of a k-slice as the tensor core sees it.
+// fp32 rows are first rounded to TF32 (round to nearest, in place): the tensor core would otherwise TRUNCATE
+// the low 13 mantissa bits, which shrinks every distance by ~1e-3 relative (a bias, not noise).
 template <bool TF32>
-__device__ __forceinline__ float row_sumsq(const uint8_t* row, int lane) {
+__device__ __forceinline__ float row_sumsq(uint8_t* row, int lane) {
   float acc = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     // rotate the 16-byte chunk order by lane so that the 8 lanes of a phase hit distinct bank groups
-    const uint4 q = *reinterpret_cast<const uint4*>(row + (((c + lane) & 7) << 4));
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint4* qp = reinterpret_cast<uint4*>(row + (((c + lane) & 7) << 4));
+    const uint4 q = *qp;
+    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    if constexpr (TF32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = (w[i] + 0x1000u) & 0xFFFFE000u;
+      *qp = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if constexpr (TF32) {
-        const float v = __uint_as_float(w[i] & 0xFFFFE000u);
+        const float v = __uint_as_float(w[i]);
         acc = fmaf(v, v, acc);
       } else {
         const float lo = __uint_as_float(w[i] << 16);
@@ -121,6 +130,7 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
     for (int i = 0; i < P.stages; ++i) {
       mbar_init(&sh.full[i], 1);
       mbar_init(&sh.empty[i], 1 + kEpiThreads / 32);
+      mbar_init(&sh.conv[i], kEpiThreads / 32);
     }
     mbar_init(&sh.tmem_full, 1);
     mbar_init(&sh.tmem_empty, kEpiThreads / 32);
@@ -205,7 +215,7 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
         for (int ks = 0; ks < P.n_kslices; ++ks, ++it) {
           const int st = it % P.stages;
           const uint32_t ph = (it / P.stages) & 1;
-          mbar_wait(&sh.full[st], ph);
+          mbar_wait(TF32 ? &sh.conv[st] : &sh.full[st], ph);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t b_addr = smem_u32(tiles + static_cast<size_t>(st) * P.stage_bytes);
@@ -249,11 +259,15 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
           const int st = it % P.stages;
           const uint32_t ph = (it / P.stages) & 1;
           mbar_wait(&sh.full[st], ph);
-          const uint8_t* bt = tiles + static_cast<size_t>(st) * P.stage_bytes;
+          uint8_t* bt = tiles + static_cast<size_t>(st) * P.stage_bytes;
           if (t < n_umma) ssb += row_sumsq<TF32>(bt + t * kSliceBytes, lane);
           if (!diag && t < rows_here) ssa += row_sumsq<TF32>(bt + kTileBytes + t * kSliceBytes, lane);
+          if constexpr (TF32) fence_proxy_async_smem();  // the rounded tile must be visible to the tensor core
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sh.empty[st]);
+          if (lane == 0) {
+            if constexpr (TF32) mbar_arrive(&sh.conv[st]);
+            mbar_arrive(&sh.empty[st]);
+          }
         }
         sh.colq[t] = row_quantity(P.mode, ssb, P.c2);
         sh.rowq[t] = row_quantity(P.mode, diag ? ssb : ssa, P.c2);

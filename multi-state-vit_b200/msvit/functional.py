@@ -244,3 +244,78 @@ def kmeans(V: torch.Tensor, n_clusters: Optional[int] = None, *, eigvals: Option
 def pool(x: torch.Tensor, labels: torch.Tensor, K: int):
     """Cluster-mean pooling: x [B, N, D], labels [B, N] int64 -> (pooled [B, K, D] fp32, counts [B, K] int32)."""
     return ops.pool(x.contiguous(), labels.contiguous(), int(K))
+
+
+@dataclass
+class HostResult:
+    labels: torch.Tensor   # [B, N] int64, pinned host memory
+    pooled: torch.Tensor   # [B, K, D] fp32, pinned host memory
+    counts: torch.Tensor   # [B, K] int32, pinned host memory
+
+
+class HostClusterer:
+    """End-to-end form of the hot path for tokens that live in HOST memory.
+
+    `run(x_host)` streams the batch to the GPU in chunks over `n_streams` CUDA streams -- pinned host tokens ->
+    H2D copy -> the kernel sequence of ClusterPlan -> D2H copy of labels, pooled tokens and counts -- so that the
+    copies of one chunk overlap the kernels of another.  Everything (device buffers, plans, pinned result buffers)
+    is allocated once; `run` returns after all chunks have landed in the pinned result buffers.
+    """
+
+    def __init__(self, B: int, N: int, D: int, dtype: torch.dtype = torch.float32, device="cuda", *, chunk: int = 128,
+                 n_streams: int = 3, **plan_kwargs):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("msvit.HostClusterer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.B, self.N, self.D, self.dtype, self.device = int(B), int(N), int(D), dtype, dev
+        self.chunk = max(1, min(int(chunk), self.B))
+        self.bounds = [(b0, min(self.B, b0 + self.chunk)) for b0 in range(0, self.B, self.chunk)]
+        n_streams = max(1, min(int(n_streams), len(self.bounds)))
+        if plan_kwargs.get("n_parents", 1) != 1:
+            raise ValueError("HostClusterer clusters whole images (single parent)")
+        self.streams, self.plans, self.xdev = [], [], []
+        self.tail_plan = self.tail_x = None
+        with torch.cuda.device(dev):
+            for _ in range(n_streams):
+                self.streams.append(torch.cuda.Stream(dev))
+                self.plans.append(ClusterPlan(self.chunk, N, D, dtype, dev, **plan_kwargs))
+                self.xdev.append(torch.empty(self.chunk, N, D, dtype=dtype, device=dev))
+            tail = self.bounds[-1][1] - self.bounds[-1][0]
+            if tail != self.chunk:
+                self.tail_plan = ClusterPlan(tail, N, D, dtype, dev, **plan_kwargs)
+                self.tail_x = torch.empty(tail, N, D, dtype=dtype, device=dev)
+            Kp = self.plans[0].Kp
+            self.labels = torch.empty(B, N, dtype=torch.int64).pin_memory()
+            self.pooled = torch.empty(B, Kp, D, dtype=torch.float32).pin_memory()
+            self.counts = torch.empty(B, Kp, dtype=torch.int32).pin_memory()
+        self.h2d_bytes = B * N * D * (4 if dtype == torch.float32 else 2)
+        self.d2h_bytes = self.labels.numel() * 8 + self.pooled.numel() * 4 + self.counts.numel() * 4
+
+    def run(self, x_host: torch.Tensor) -> HostResult:
+        if x_host.is_cuda:
+            raise ValueError("HostClusterer.run takes host tokens; use cluster_tokens / ClusterPlan for device tensors")
+        if tuple(x_host.shape) != (self.B, self.N, self.D) or x_host.dtype != self.dtype:
+            raise ValueError(f"expected host tokens {(self.B, self.N, self.D)} {self.dtype}")
+        if not x_host.is_pinned():
+            x_host = x_host.pin_memory()
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for i, (b0, b1) in enumerate(self.bounds):
+            j = i % len(self.streams)
+            st = self.streams[j]
+            if i < len(self.streams):
+                st.wait_event(start)
+            full = (b1 - b0) == self.chunk
+            plan = self.plans[j] if full else self.tail_plan
+            xd = self.xdev[j] if full else self.tail_x
+            with torch.cuda.stream(st):
+                xd.copy_(x_host[b0:b1], non_blocking=True)
+                out = plan.run(xd)
+                self.labels[b0:b1].copy_(out.labels, non_blocking=True)
+                self.pooled[b0:b1].copy_(out.pooled, non_blocking=True)
+                self.counts[b0:b1].copy_(out.counts, non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        cur.synchronize()
+        return HostResult(self.labels, self.pooled, self.counts)

@@ -272,6 +272,13 @@ def truncate_to_tf32(x: torch.Tensor) -> torch.Tensor:
     return (xi & ~0x1FFF).view(torch.float32).to(x.dtype)
 
 
+def round_to_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round to nearest TF32 (10 explicit mantissa bits), ties away from zero: what the affinity kernel feeds the
+    tensor core for an fp32 operand."""
+    xi = x.to(torch.float32).contiguous().view(torch.int32)
+    return ((xi + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)
+
+
 def subspace_distance(V: torch.Tensor, W: torch.Tensor) -> float:
     """|V V^T - W W^T|_F for orthonormal column blocks."""
     return float(torch.linalg.norm(V @ V.T - W @ W.T).item())

@@ -26,7 +26,7 @@ RTOL = 1e-3
 
 
 def as_seen_by_tensor_core(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    return O.round_to_bf16(x) if dtype == torch.bfloat16 else O.truncate_to_tf32(x)
+    return O.round_to_bf16(x) if dtype == torch.bfloat16 else O.round_to_tf32(x)
 
 
 def canon(labels: torch.Tensor) -> torch.Tensor:
@@ -199,7 +199,7 @@ def test_cluster_tokens_threshold_mode_and_golden(golden_dir):
     np.testing.assert_allclose(out.pooled[0, :, :16].cpu().numpy(), g["pooled_sample"], rtol=RTOL, atol=1e-5)
     # eigenvalue-threshold selection of the number of children (modeling_spectral.py:87)
     thr = msvit.cluster_tokens(x[None].to(DEV), ncut_dim=K, eigenvalue_threshold=0.1, scale=float(g["scale"]))
-    child, _, _, nc = O.cluster_tokens(O.truncate_to_tf32(x[None]).double(), None, ncut_dim=K,
+    child, _, _, nc = O.cluster_tokens(O.round_to_tf32(x[None]).double(), None, ncut_dim=K,
                                        eigenvalue_threshold=0.1, scale=float(g["scale"]))
     assert thr.n_child.cpu().tolist() == nc.tolist()
     assert torch.equal(thr.labels.cpu(), child)
@@ -225,7 +225,7 @@ def test_hierarchical_reclustering_matches_oracle():
     s = default_scale(D)
     parent_gpu = None
     parent_cpu = None
-    xq = O.truncate_to_tf32(x).double()
+    xq = O.round_to_tf32(x).double()
     for level in range(3):
         out = msvit.cluster_tokens(x.to(DEV), parent_gpu, ncut_dim=4, n_clusters=2, scale=s)
         child, _, _, nc = O.cluster_tokens(xq, parent_cpu, ncut_dim=4, n_clusters=2, scale=s)
@@ -251,7 +251,7 @@ def test_ragged_and_tiny_segments():
     parent[0, 1:4] = 3         # three tokens, parent id 2 is empty
     parent[1, 10:40] = 2
     out = msvit.cluster_tokens(x.to(DEV), parent.to(DEV), ncut_dim=4, n_clusters=3, scale=default_scale(D))
-    child, _, _, nc = O.cluster_tokens(O.truncate_to_tf32(x).double(), parent, ncut_dim=4, n_clusters=3,
+    child, _, _, nc = O.cluster_tokens(O.round_to_tf32(x).double(), parent, ncut_dim=4, n_clusters=3,
                                        scale=default_scale(D))
     assert out.n_child.cpu().tolist() == nc.tolist()
     assert torch.equal(out.labels.cpu(), child)
@@ -267,7 +267,7 @@ def test_module_forward_is_a_drop_in():
     parents = torch.zeros(B, N, dtype=torch.long, device=DEV)  # msvitencoder.py:478
     child = module(parents, x.to(DEV))
     assert child.dtype == torch.int64 and child.shape == (B, N) and child.device.type == "cuda"
-    ref, _, _, _ = O.cluster_tokens(O.truncate_to_tf32(x).double(), None, ncut_dim=K, eigenvalue_threshold=0.05,
+    ref, _, _, _ = O.cluster_tokens(O.round_to_tf32(x).double(), None, ncut_dim=K, eigenvalue_threshold=0.05,
                                     scale=default_scale(D))
     assert torch.equal(child.cpu(), ref)
     n_child = child.max(dim=1).values + 1  # what the caller computes (msvitencoder.py:491)

@@ -76,7 +76,7 @@ def stage_eig():
 def stage_affinity(dtype):
     for (B, N, D) in [(2, 196, 768), (2, 64, 64), (1, 300, 128), (1, 576, 1024), (2, 37, 24)]:
         x, _ = planted_tokens(B, N, D, 4)
-        xq = O.round_to_bf16(x) if dtype == torch.bfloat16 else O.truncate_to_tf32(x)
+        xq = O.round_to_bf16(x) if dtype == torch.bfloat16 else O.round_to_tf32(x)
         try:
             A, deg = F.affinity(x.to(dtype).to(DEV), "rbf", 3.0, default_scale(D))
             torch.cuda.synchronize()
@@ -104,7 +104,7 @@ def stage_e2e():
     for dt in (torch.float32, torch.bfloat16):
         out = msvit.cluster_tokens(x.to(dt).to(DEV), ncut_dim=K, n_clusters=K, scale=default_scale(D))
         torch.cuda.synchronize()
-        xq = O.round_to_bf16(x) if dt == torch.bfloat16 else O.truncate_to_tf32(x)
+        xq = O.round_to_bf16(x) if dt == torch.bfloat16 else O.round_to_tf32(x)
         child, _, lam, _ = O.cluster_tokens(xq.double(), None, ncut_dim=K, n_clusters=K, scale=default_scale(D))
         print("e2e", dt, "labels equal", torch.equal(out.labels.cpu(), child), "iters", out.iters.flatten().cpu().tolist())
         print("   lam err", relerr(out.eigvals[:, 0], lam[:, 0]))

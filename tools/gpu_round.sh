@@ -1,0 +1,47 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, smoke, bench, then (optionally) the ncu launch list and a full capture.
+#   tools/gpu_round.sh [tests] [bench] [launches] [full:<kernel-regex>]
+# Everything is written under gpurun_out/.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+for what in "$@"; do
+  case "$what" in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+      echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+      tail -5 gpurun_out/pytest_gpu.log
+      ;;
+    smoke)
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+      echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
+      ;;
+    bench)
+      timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+      echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+      ;;
+    benchref)
+      timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+      echo "benchref rc=$?"; cat gpurun_out/bench_ref.json
+      ;;
+    launches)
+      CMD="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --cpu-images 8"
+      timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
+      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+          --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+      echo "launches rc=$?"
+      ;;
+    full:*)
+      KREGEX="${what#full:}"
+      CMD="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --cpu-images 8"
+      timeout 600 $CMD > gpurun_out/plain_full.log 2>&1 &&
+      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 3 -c 1 \
+          -f -o "gpurun_out/prof_${KREGEX}" $CMD > gpurun_out/ncu_full_${KREGEX}.log 2>&1
+      echo "full ${KREGEX} rc=$?"
+      ;;
+    debug:*)
+      timeout 600 python tools/gpu_debug.py "${what#debug:}" 2>&1 | tee -a gpurun_out/debug.log
+      ;;
+  esac
+done
