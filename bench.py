@@ -207,6 +207,7 @@ def run_ours(args):
     import torch.distributed as dist
     import msvit
     from msvit.functional import ClusterPlan, HostClusterer
+    from msvit.sharding import max_over_ranks
     from msvit.synthetic import default_scale, planted_tokens
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -242,11 +243,7 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     def reduce_max(v: float) -> float:
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return max_over_ranks(v, dev)
 
     # ---- device-resident timing: K steps, per-stage events recorded inside the same region
     for _ in range(args.warmup):
