@@ -10,9 +10,13 @@
 // so the affinity is used exactly as stored (no scaled copy) and only two n x m blocks (U, Y) live in
 // shared memory next to A.  Per iteration:
 //     Y = D^-1 (A U)                          4x4 register tiles, A read through its symmetric column
-//     every rr_every-th iteration:            H = U^T D Y, parallel-order Jacobi on one warp, rotate U and Y,
-//                                             residuals |Abar v - theta v| for the k wanted pairs
-//     U = Y L^-T,  L L^T = Y^T D Y            Cholesky QR in the D inner product (repeated if ill conditioned)
+//     H = U^T D Y                             and the cheap trigger: column residuals |y_j - U h_j|_D of the k leading
+//                                             columns plus their coupling to the trailing ones (ordered iteration)
+//     when the trigger fires (or every rr_every-th iteration): Rayleigh-Ritz -- block-wide parallel-order Jacobi
+//                                             on H (one matrix entry per thread, one barrier per round), rotate U
+//                                             and Y, true residuals |Abar v - theta v| of the k wanted pairs
+//     U = Y L^-T,  L L^T = Y^T D Y            Cholesky QR in the D inner product (register Cholesky on one warp,
+//                                             rows exchanged by shuffles; repeated if ill conditioned)
 // Dot products are reduced with warp shuffles; nothing is atomically accumulated, so results are
 // bit-reproducible run to run.
 #include "common.cuh"
@@ -21,7 +25,13 @@
 namespace msvit {
 namespace eig {
 
-constexpr int kThreads = 256;
+#ifndef EIG_THREADS
+#define EIG_THREADS 256
+#endif
+#ifndef EIG_MINBLOCKS
+#define EIG_MINBLOCKS 1
+#endif
+constexpr int kThreads = EIG_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kScratchFloats = 4096;  // 16 KB partial-sum scratch for the m x m Gram reductions
 
@@ -43,7 +53,7 @@ struct Params {
 
 struct Layout {
   // offsets in floats from the dynamic shared memory base
-  int As, Us, Ys, Gs, Ss, dg, scratch, misc, total;
+  int As, Us, Ys, Gs, Ss, dg, scratch, misc, jac, ptab, total;
 };
 
 __host__ __device__ inline Layout make_layout(int N, int m, bool resident) {
@@ -57,6 +67,8 @@ __host__ __device__ inline Layout make_layout(int N, int m, bool resident) {
   L.dg = o;       o += round_up(N, 4);
   L.scratch = o;  o += kScratchFloats;
   L.misc = o;     o += 6 * MSVIT_MAX_EIG_BLOCK;
+  L.jac = o;      o += 4 * m * m;                      // Jacobi ping-pong: H[2][m*m], S[2][m*m]
+  L.ptab = o;     o += (m * m + 3) / 4;                // round-robin partner table, (m-1) x m bytes
   L.total = o;
   return L;
 }
@@ -151,32 +163,46 @@ __device__ __forceinline__ void weighted_gram(const float* __restrict__ Ps, cons
   __syncthreads();
 }
 
-// In-place Cholesky of the leading me x me block of G (row stride m + 1) by warp 0; L is left in the lower
-// triangle.  Returns (to every thread) the smallest pivot of the unit-diagonal-scaled matrix, i.e. a
-// conditioning estimate that ignores column scaling.  Non-positive pivots zero the column (rank deficiency).
+// In-place Cholesky of the leading me x me block of G (row stride m + 1) by warp 0: lane i keeps row i in
+// registers, row j is broadcast by shuffles (left-looking), L is written back to the lower triangle.
+// Returns (to every thread) the smallest pivot of the unit-diagonal-scaled matrix, i.e. a conditioning
+// estimate that ignores column scaling.  Non-positive pivots zero the column (rank deficiency).
+template <int MB>
 __device__ __forceinline__ float cholesky(float* __restrict__ G, int m, int me, float* __restrict__ misc) {
   const int ld = m + 1;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
+    const int row = lane < me ? lane : 0;
+    float g[MB];
+#pragma unroll
+    for (int c = 0; c < MB; ++c) g[c] = (c < me) ? G[row * ld + c] : 0.f;
     float minpiv = 1.0f;
-    for (int j = 0; j < me; ++j) {
-      // column j: L[i][j] = (G[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j]
-      float gjj = G[j * ld + j];
-      float s = gjj;
-      for (int k2 = 0; k2 < j; ++k2) s = fmaf(-G[j * ld + k2], G[j * ld + k2], s);
-      const float rel = gjj > 0.f ? s / gjj : 0.f;
-      const bool ok = rel > 1e-6f && s > 0.f;
-      minpiv = fminf(minpiv, ok ? rel : 1.0f);
-      const float ljj = ok ? sqrtf(s) : 0.f;
-      const float inv = ok ? 1.0f / ljj : 0.f;
-      __syncwarp();
-      for (int i = j + 1 + lane; i < me; i += 32) {
-        float t = G[i * ld + j];
-        for (int k2 = 0; k2 < j; ++k2) t = fmaf(-G[i * ld + k2], G[j * ld + k2], t);
-        G[i * ld + j] = t * inv;
+#pragma unroll
+    for (int j = 0; j < MB; ++j) {
+      if (j < me) {  // warp-uniform
+        // s_i = G[i][j] - sum_{c<j} L[i][c] L[j][c]; lane j's value is the pivot
+        float s0 = g[j], s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c + 1 < j; c += 2) {
+          s0 = fmaf(-g[c], __shfl_sync(0xffffffffu, g[c], j), s0);
+          s1 = fmaf(-g[c + 1], __shfl_sync(0xffffffffu, g[c + 1], j), s1);
+        }
+        if (j & 1) s0 = fmaf(-g[j - 1], __shfl_sync(0xffffffffu, g[j - 1], j), s0);
+        const float s = s0 + s1;
+        const float piv = __shfl_sync(0xffffffffu, s, j);
+        const float gjj = __shfl_sync(0xffffffffu, g[j], j);
+        const float rel = gjj > 0.f ? piv / gjj : 0.f;
+        const bool ok = rel > 1e-6f && piv > 0.f;
+        minpiv = fminf(minpiv, ok ? rel : 1.0f);
+        const float ljj = ok ? sqrtf(piv) : 0.f;
+        const float inv = ok ? 1.0f / ljj : 0.f;
+        g[j] = lane == j ? ljj : (lane > j ? s * inv : 0.f);
       }
-      if (lane == 0) G[j * ld + j] = ljj;
-      __syncwarp();
+    }
+    if (lane < me) {
+#pragma unroll
+      for (int c = 0; c < MB; ++c)
+        if (c <= lane && c < me) G[lane * ld + c] = g[c];
     }
     if (lane == 0) misc[0] = minpiv;
   }
@@ -210,89 +236,108 @@ __device__ __forceinline__ void trisolve_rows(float* __restrict__ Xs, const floa
   __syncthreads();
 }
 
-// Symmetric eigen-decomposition of H (m x m, row stride m + 1, m even) by warp 0: parallel-order
-// two-sided Jacobi.  On exit H's diagonal holds the eigenvalues and Sm (same stride) the eigenvectors
-// (columns).  Every round applies m/2 disjoint rotations; the 2x2 blocks of J^T H J are independent.
-__device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int m,
-                                       float* __restrict__ cs) {
-  const int ld = m + 1;
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const int half = m >> 1;
-    for (int e = lane; e < m * m; e += 32) Sm[(e / m) * ld + (e % m)] = (e / m == e % m) ? 1.f : 0.f;
-    // symmetrise
-    for (int e = lane; e < m * m; e += 32) {
-      const int a = e / m, b = e % m;
-      if (a < b) {
-        const float v = 0.5f * (H[a * ld + b] + H[b * ld + a]);
-        H[a * ld + b] = v;
-        H[b * ld + a] = v;
+// Round-robin tournament: partner of player i in round r (m even players, m - 1 rounds).
+__device__ __forceinline__ int rr_partner(int i, int r, int m) {
+  if (i == m - 1) return r;
+  int j = 2 * r - i;
+  if (j < 0) j += m - 1;
+  if (j >= m - 1) j -= m - 1;
+  return j == i ? m - 1 : j;
+}
+
+// Jacobi rotation that annihilates the (p, q) entry: J = [[c, s], [-s, c]] on (p, q), H' = J^T H J.
+__device__ __forceinline__ void jacobi_rot(float app, float aqq, float apq, float& c, float& s, bool& big) {
+  c = 1.f;
+  s = 0.f;
+  const float scale = sqrtf(fabsf(app * aqq));
+  const float aabs = fabsf(apq);
+  if (aabs > 1e-30f && aabs > 1e-9f * scale) {
+    const float delta = 0.5f * (aqq - app);
+    const float r = sqrtf(fmaf(delta, delta, apq * apq));
+    const float t = (delta >= 0.f ? apq : -apq) / (fabsf(delta) + r);
+    c = rsqrtf(fmaf(t, t, 1.f));
+    c = c * (1.5f - 0.5f * fmaf(t, t, 1.f) * c * c);  // one Newton step: c^2 + s^2 = 1 to fp32 accuracy
+    s = t * c;
+  }
+  big = big || aabs > fmaxf(1e-4f * scale, 3e-8f);
+}
+
+// Symmetric eigen-decomposition of H (m x m, row stride m + 1, m even) by the whole CTA: parallel-order
+// two-sided Jacobi with one matrix entry per thread and one barrier per round (ping-pong buffers).
+// On exit H's diagonal holds the eigenvalues and Sm (same stride) the eigenvectors (columns).
+// A sweep whose rotations were all below 1e-4 (relative) ends the iteration: convergence is quadratic.
+__device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int m, float* __restrict__ jac,
+                                       const uint8_t* __restrict__ ptab) {
+  const int ld = m + 1, mm = m * m;
+  float* JH = jac;           // [2][mm]
+  float* JS = jac + 2 * mm;  // [2][mm]
+  for (int e = threadIdx.x; e < mm; e += kThreads) {
+    const int a = e / m, b = e - a * m;
+    JH[e] = 0.5f * (H[a * ld + b] + H[b * ld + a]);
+    JS[e] = a == b ? 1.f : 0.f;
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int sweep = 0; sweep < 10; ++sweep) {
+    bool big = false;
+    for (int r = 0; r < m - 1; ++r) {
+      const float* __restrict__ hin = JH + cur * mm;
+      const float* __restrict__ sin_ = JS + cur * mm;
+      float* __restrict__ hout = JH + (cur ^ 1) * mm;
+      float* __restrict__ sout = JS + (cur ^ 1) * mm;
+      for (int e = threadIdx.x; e < mm; e += kThreads) {
+        const int a = e / m, b = e - a * m;
+        const int pa = ptab[r * m + a], pb = ptab[r * m + b];
+        const int p1 = min(a, pa), q1 = max(a, pa), p2 = min(b, pb), q2 = max(b, pb);
+        float c1, s1, c2, s2;
+        bool dummy = false;
+        jacobi_rot(hin[p1 * m + p1], hin[q1 * m + q1], hin[p1 * m + q1], c1, s1, dummy);
+        jacobi_rot(hin[p2 * m + p2], hin[q2 * m + q2], hin[p2 * m + q2], c2, s2, big);
+        const float g1 = a < pa ? -s1 : s1;  // coefficient of the partner row
+        const float g2 = b < pb ? -s2 : s2;  // coefficient of the partner column
+        const float v = c1 * fmaf(g2, hin[a * m + pb], c2 * hin[e]) + g1 * fmaf(g2, hin[pa * m + pb], c2 * hin[pa * m + b]);
+        hout[e] = pa == b ? 0.f : v;
+        sout[e] = fmaf(g2, sin_[a * m + pb], c2 * sin_[e]);
       }
+      cur ^= 1;
+      if (r < m - 2) __syncthreads();
     }
-    __syncwarp();
-    for (int sweep = 0; sweep < 12; ++sweep) {
-      float off = 0.f, dia = 0.f;
-      for (int r = 0; r < m - 1; ++r) {
-        // rotation angles of this round's pairs
-        for (int t = lane; t < half; t += 32) {
-          int p, q;
-          if (t == 0) { p = r; q = m - 1; }
-          else { p = (r + t) % (m - 1); q = (r - t + (m - 1)) % (m - 1); }
-          if (p > q) { const int x = p; p = q; q = x; }
-          const float app = H[p * ld + p], aqq = H[q * ld + q], apq = H[p * ld + q];
-          float c = 1.f, s = 0.f;
-          off = fmaf(apq, apq, off);
-          if (fabsf(apq) > 1e-30f && fabsf(apq) > 1e-9f * sqrtf(fabsf(app * aqq))) {
-            const float tau = (aqq - app) / (2.f * apq);
-            const float tt = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-            c = rsqrtf(1.f + tt * tt);
-            s = tt * c;
-          }
-          cs[4 * t + 0] = c;
-          cs[4 * t + 1] = s;
-          cs[4 * t + 2] = __int_as_float(p);
-          cs[4 * t + 3] = __int_as_float(q);
-        }
-        __syncwarp();
-        // H[P][P'] <- J_P^T H[P][P'] J_P'   with J = [[c, s], [-s, c]] on (p, q)
-        for (int b2 = lane; b2 < half * half; b2 += 32) {
-          const int t1 = b2 / half, t2 = b2 % half;
-          const float c1 = cs[4 * t1], s1 = cs[4 * t1 + 1];
-          const int p1 = __float_as_int(cs[4 * t1 + 2]), q1 = __float_as_int(cs[4 * t1 + 3]);
-          const float c2 = cs[4 * t2], s2 = cs[4 * t2 + 1];
-          const int p2 = __float_as_int(cs[4 * t2 + 2]), q2 = __float_as_int(cs[4 * t2 + 3]);
-          const float hpp = H[p1 * ld + p2], hpq = H[p1 * ld + q2], hqp = H[q1 * ld + p2], hqq = H[q1 * ld + q2];
-          // rows: J1^T
-          const float rpp = c1 * hpp - s1 * hqp, rpq = c1 * hpq - s1 * hqq;
-          const float rqp = s1 * hpp + c1 * hqp, rqq = s1 * hpq + c1 * hqq;
-          // columns: J2
-          float npp = c2 * rpp - s2 * rpq, npq = s2 * rpp + c2 * rpq;
-          float nqp = c2 * rqp - s2 * rqq, nqq = s2 * rqp + c2 * rqq;
-          if (t1 == t2) { npq = 0.f; nqp = 0.f; }
-          H[p1 * ld + p2] = npp; H[p1 * ld + q2] = npq; H[q1 * ld + p2] = nqp; H[q1 * ld + q2] = nqq;
-        }
-        // S[:, P'] <- S[:, P'] J_P'
-        for (int e = lane; e < m * half; e += 32) {
-          const int a = e / half, t2 = e % half;
-          const float c2 = cs[4 * t2], s2 = cs[4 * t2 + 1];
-          const int p2 = __float_as_int(cs[4 * t2 + 2]), q2 = __float_as_int(cs[4 * t2 + 3]);
-          const float sp = Sm[a * ld + p2], sq = Sm[a * ld + q2];
-          Sm[a * ld + p2] = c2 * sp - s2 * sq;
-          Sm[a * ld + q2] = s2 * sp + c2 * sq;
-        }
-        __syncwarp();
-      }
-      for (int a = lane; a < m; a += 32) dia = fmaf(H[a * ld + a], H[a * ld + a], dia);
-      off = warp_sum(off);
-      dia = warp_sum(dia);
-      if (off <= 1e-14f * dia) break;
+    if (!__syncthreads_or(big ? 1 : 0)) break;
+  }
+  const float* __restrict__ hf = JH + cur * mm;
+  const float* __restrict__ sf = JS + cur * mm;
+  for (int e = threadIdx.x; e < mm; e += kThreads) {
+    const int a = e / m, b = e - a * m;
+    H[a * ld + b] = hf[e];
+    Sm[a * ld + b] = sf[e];
+  }
+  __syncthreads();
+}
+
+// Residuals of the leading columns against span(U) or against their Ritz values, reduced per column:
+// out[c] = sum_i dg[i] * r_ic^2.  Warp shuffle reduction, then a fixed-order sum over warps (deterministic).
+template <int MB>
+__device__ __forceinline__ void reduce_columns(const float (&rloc)[MB], int ncols, float* __restrict__ scratch,
+                                               float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < MB; ++c) {
+    if (c < ncols) {
+      const float v = warp_sum(rloc[c]);
+      if (lane == 0) scratch[warp * MSVIT_MAX_EIG_BLOCK + c] = v;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < ncols) {
+    float v = 0.f;
+    for (int w = 0; w < kWarps; ++w) v += scratch[w * MSVIT_MAX_EIG_BLOCK + threadIdx.x];
+    out[threadIdx.x] = v;
   }
   __syncthreads();
 }
 
 template <int MB, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const Params P) {
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t load_bar;
   const Layout L = make_layout(P.N, P.m, RESIDENT);
@@ -303,11 +348,12 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
   float* Ss = smem + L.Ss;
   float* dg = smem + L.dg;
   float* scratch = smem + L.scratch;
-  float* misc = smem + L.misc;           // [0] = scalar broadcast
+  float* misc = smem + L.misc;           // [0] = scalar broadcast, [1] = worst residual, [2] = trigger flag
   float* theta = misc + 8;               // [m] Ritz values in sorted order
-  float* res = theta + MSVIT_MAX_EIG_BLOCK;   // [m] squared residuals
+  float* res = theta + MSVIT_MAX_EIG_BLOCK;   // [m] squared residuals / column signs
   int* order = reinterpret_cast<int*>(res + MSVIT_MAX_EIG_BLOCK);  // [m] sorted position -> Jacobi column
-  float* cs = misc + 8 + 3 * MSVIT_MAX_EIG_BLOCK;  // 4 * m/2 rotation records
+  float* jac = smem + L.jac;
+  uint8_t* ptab = reinterpret_cast<uint8_t*>(smem + L.ptab);
 
   const int m = P.m, k = P.k;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
     mbar_init(&load_bar, 1);
     fence_mbar_init();
   }
+  for (int e = threadIdx.x; e < (m - 1) * m; e += kThreads) ptab[e] = static_cast<uint8_t>(rr_partner(e % m, e / m, m));
   __syncthreads();
   uint32_t load_phase = 0;
 
@@ -331,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
     const float* Ag = P.A + g.a0;
     const int lda = g.lda;
     const int me = n < m ? n : m;  // effective block width
+    const int kk = k < me ? k : me;  // wanted pairs that exist
 
     // ---- load: affinity block (bulk async copy), degree, start block
     if constexpr (RESIDENT) {
@@ -357,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
 
     // ---- D-orthonormalise the start block
     weighted_gram(Us, Us, dg, n, m, Gs, scratch);
-    cholesky(Gs, m, me, misc);
+    cholesky<MB>(Gs, m, me, misc);
     trisolve_rows<MB>(Us, Us, n, m, me, Gs);
 
     if constexpr (RESIDENT) {
@@ -373,10 +421,46 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
       matvec<RESIDENT>(Amat, lda, n, m, Us, Ys, dg);
       __syncthreads();
       const bool last = it >= P.max_iter || n <= m;  // n <= m: span(U) is the whole space, one step is exact
-      if (last || (it % P.rr_every) == 0) {
+      // ---- H = U^T D Y (U is D-orthonormal) and the trigger: for each wanted column j
+      //        |y_j - U h_j|_D^2 + sum_{a >= kk} H[a][j]^2   =   residual of the Ritz problem on the leading columns
+      weighted_gram(Us, Ys, dg, n, m, Gs, scratch);
+      bool do_rr = last || (it % P.rr_every) == 0;
+      if (!do_rr && it >= 2) {
+        float rloc[MB];
+#pragma unroll
+        for (int c = 0; c < MB; ++c) rloc[c] = 0.f;
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+          float u[MB];
+#pragma unroll
+          for (int a = 0; a < MB; ++a) u[a] = a < m ? Us[i * m + a] : 0.f;
+          const float d = dg[i];
+#pragma unroll
+          for (int c = 0; c < MB; ++c) {
+            if (c < kk) {
+              float r = Ys[i * m + c];
+#pragma unroll
+              for (int a = 0; a < MB; ++a)
+                if (a < m) r = fmaf(-u[a], Gs[a * (m + 1) + c], r);
+              rloc[c] = fmaf(d * r, r, rloc[c]);
+            }
+          }
+        }
+        reduce_columns<MB>(rloc, kk, scratch, res);
+        if (threadIdx.x == 0) {
+          float worst = 0.f;
+          for (int c = 0; c < kk; ++c) {
+            float v = res[c];
+            for (int a = kk; a < me; ++a) v = fmaf(Gs[a * (m + 1) + c], Gs[a * (m + 1) + c], v);
+            if (Gs[c * (m + 1) + c] >= P.lam_floor) worst = fmaxf(worst, v);
+          }
+          misc[2] = worst <= tol2 ? 1.f : 0.f;
+        }
+        __syncthreads();
+        do_rr = misc[2] != 0.f;
+      }
+      if (do_rr) {
         // ---- Rayleigh-Ritz on span(U)
-        weighted_gram(Us, Ys, dg, n, m, Gs, scratch);
-        jacobi(Gs, Ss, m, cs);
+        jacobi(Gs, Ss, m, jac, ptab);
         if (threadIdx.x < m) {
           const int a = threadIdx.x;
           const float ta = Gs[a * (m + 1) + a];
@@ -387,7 +471,6 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
           }
           order[rank] = a;
           theta[rank] = ta;
-          res[a] = 0.f;
         }
         __syncthreads();
         // rotate U and Y into the Ritz basis, accumulate weighted residuals of the wanted pairs
@@ -422,23 +505,11 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
             }
           }
         }
-        // per-column residual: warp shuffle reduction, then a fixed-order sum over warps
-#pragma unroll
-        for (int c = 0; c < MB; ++c) {
-          if (c < k) {
-            const float v = warp_sum(rloc[c]);
-            if (lane == 0) scratch[warp * MSVIT_MAX_EIG_BLOCK + c] = v;
-          }
-        }
-        __syncthreads();
+        reduce_columns<MB>(rloc, kk, scratch, res);
         if (threadIdx.x == 0) {
           float worst = 0.f;
-          const int kk = k < me ? k : me;
-          for (int c = 0; c < kk; ++c) {
-            float v = 0.f;
-            for (int w = 0; w < kWarps; ++w) v += scratch[w * MSVIT_MAX_EIG_BLOCK + c];
-            if (theta[c] >= P.lam_floor) worst = fmaxf(worst, v);
-          }
+          for (int c = 0; c < kk; ++c)
+            if (theta[c] >= P.lam_floor) worst = fmaxf(worst, res[c]);
           misc[1] = worst;
         }
         __syncthreads();
@@ -446,11 +517,11 @@ __global__ void __launch_bounds__(kThreads, 1) ncut_eig_kernel(const Params P) {
       }
       // ---- U = orth_D(Y)
       weighted_gram(Ys, Ys, dg, n, m, Gs, scratch);
-      const float piv = cholesky(Gs, m, me, misc);
+      const float piv = cholesky<MB>(Gs, m, me, misc);
       trisolve_rows<MB>(Us, Ys, n, m, me, Gs);
       if (piv < 0.05f) {
         weighted_gram(Us, Us, dg, n, m, Gs, scratch);
-        cholesky(Gs, m, me, misc);
+        cholesky<MB>(Gs, m, me, misc);
         trisolve_rows<MB>(Us, Us, n, m, me, Gs);
       }
     }
@@ -530,9 +601,12 @@ extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float*
   P.max_iter = max_iter; P.rr_every = 3; P.tol = tol; P.lam_floor = lam_floor;
   size_t smem = static_cast<size_t>(make_layout(N, block, true).total) * 4;
   P.a_resident = smem <= kMaxSmem ? 1 : 0;
+#ifdef EIG_FORCE_STREAM
+  P.a_resident = 0;
+#endif
   if (!P.a_resident) smem = static_cast<size_t>(make_layout(N, block, false).total) * 4;
   if (smem > kMaxSmem) return MSVIT_ERR_SHAPE;
-  const int grid = S < 4 * sm_count() ? S : 4 * sm_count();
+  const int grid = S < 8 * sm_count() ? S : 8 * sm_count();
   if (block <= 16) return launch<16>(P, grid, smem, stream);
   return launch<32>(P, grid, smem, stream);
 }
