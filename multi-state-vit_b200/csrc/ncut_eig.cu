@@ -7,33 +7,33 @@
 //
 // The iteration runs in the "random walk" coordinates u = D^-1/2 v:
 //     Abar v = lam v   <=>   D^-1 A u = lam u,      v-orthonormal  <=>  u^T D u = I
-// so the affinity is used exactly as stored (no scaled copy) and only two n x m blocks (U, Y) live in
-// shared memory next to A.  Per iteration:
-//     Y = D^-1 (A U)                          4x4 register tiles, A read through its symmetric column
-//     H = U^T D Y                             and the cheap trigger: column residuals |y_j - U h_j|_D of the k leading
-//                                             columns plus their coupling to the trailing ones (ordered iteration)
-//     when the trigger fires (or every rr_every-th iteration): Rayleigh-Ritz -- block-wide parallel-order Jacobi
-//                                             on H (one matrix entry per thread, one barrier per round), rotate U
-//                                             and Y, true residuals |Abar v - theta v| of the k wanted pairs
-//     U = Y L^-T,  L L^T = Y^T D Y            Cholesky QR in the D inner product (register Cholesky on one warp,
-//                                             rows exchanged by shuffles; repeated if ill conditioned)
-// Dot products are reduced with warp shuffles; nothing is atomically accumulated, so results are
-// bit-reproducible run to run.
+// so the affinity is used exactly as stored (no scaled copy).  The n x m blocks U and Y live in shared
+// memory TRANSPOSED (row c = column c of the block, row stride ldt with ldt % 32 == 16, so that the
+// 128-bit fragment loads below are bank-conflict free); the affinity block itself is streamed from
+// global memory / L2 once per iteration, which keeps the CTA small enough (~37 KB, 128 threads at
+// N = 196) for several segments to be in flight per SM: the serial m x m steps of one segment
+// (Cholesky, Jacobi) overlap the tensor-core products of the others.
+//
+// Per iteration:
+//     Y = D^-1 (A U)             warp-level tensor-core MMA (mma.sync m16n8k8, TF32 operands, fp32 accumulate)
+//                                with the 3-product split  a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (a_hi = a
+//                                truncated to TF32, a_lo = a - a_hi exactly), i.e. fp32-level accuracy.
+//                                A fragments are 128-bit loads of 4 consecutive columns per lane: the k index
+//                                inside a 16-column block is permuted identically for both operands.
+//     G = Y^T D Y,  H = U^T D Y  same MMA scheme, one warp per 16 x 8 output tile
+//     trigger                    column residuals |y_j - U h_j|_D of the k leading columns plus their coupling
+//                                to the trailing ones (ordered iteration): fires the Rayleigh-Ritz step
+//     Rayleigh-Ritz (on trigger / every rr_every-th iteration): block-wide parallel-order Jacobi on H (one
+//                                matrix entry per thread, one barrier per round), rotate U and Y, true
+//                                residuals |Abar v - theta v| of the k wanted pairs
+//     U = Y L^-T,  L L^T = G     Cholesky QR in the D inner product (register Cholesky on one warp, rows
+//                                exchanged by shuffles; repeated if ill conditioned)
+// Nothing is atomically accumulated and every reduction has a fixed order: results are bit-reproducible.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace msvit {
 namespace eig {
-
-#ifndef EIG_THREADS
-#define EIG_THREADS 256
-#endif
-#ifndef EIG_MINBLOCKS
-#define EIG_MINBLOCKS 1
-#endif
-constexpr int kThreads = EIG_THREADS;
-constexpr int kWarps = kThreads / 32;
-constexpr int kScratchFloats = 4096;  // 16 KB partial-sum scratch for the m x m Gram reductions
 
 struct Params {
   const float* A;
@@ -48,27 +48,37 @@ struct Params {
   int max_iter, rr_every;
   float tol;
   float lam_floor;  // wanted pairs whose Ritz value is below this are exempt from the residual test
-  int a_resident;  // 1: the affinity block is copied into shared memory once (TMA bulk copy)
+  int fast_iters;   // the first fast_iters products use a single TF32 pass (far from convergence)
 };
 
 struct Layout {
   // offsets in floats from the dynamic shared memory base
-  int As, Us, Ys, Gs, Ss, dg, scratch, misc, jac, ptab, total;
+  int Ut, Yt, dg, dinv, Gs, Hs, Ss, pinv, misc, colred, jac, ptab, total;
+  int ldt;
 };
 
-__host__ __device__ inline Layout make_layout(int N, int m, bool resident) {
+__host__ __device__ inline int ldt_of(int N) {
+  const int np = round_up(N, 16);
+  return (np % 32 == 16) ? np : np + 16;
+}
+
+// rows: 16 or 32 rows of the transposed blocks (>= m, multiple of 16)
+__host__ __device__ inline Layout make_layout(int N, int m, int rows, int nwarps) {
   Layout L;
+  L.ldt = ldt_of(N);
   int o = 0;
-  L.As = o;       o += resident ? N * lda_of(N) : 0;
-  L.Us = o;       o += round_up(N, 4) * m;
-  L.Ys = o;       o += round_up(N, 4) * m;
-  L.Gs = o;       o += m * (m + 1);
-  L.Ss = o;       o += m * (m + 1);
-  L.dg = o;       o += round_up(N, 4);
-  L.scratch = o;  o += kScratchFloats;
-  L.misc = o;     o += 6 * MSVIT_MAX_EIG_BLOCK;
-  L.jac = o;      o += 4 * m * m;                      // Jacobi ping-pong: H[2][m*m], S[2][m*m]
-  L.ptab = o;     o += (m * m + 3) / 4;                // round-robin partner table, (m-1) x m bytes
+  L.Ut = o;      o += rows * L.ldt;
+  L.Yt = o;      o += rows * L.ldt;
+  L.dg = o;      o += round_up(N, 16);
+  L.dinv = o;    o += round_up(N, 16);
+  L.Gs = o;      o += round_up(m * (m + 1), 4);
+  L.Hs = o;      o += round_up(m * (m + 1), 4);
+  L.Ss = o;      o += round_up(m * (m + 1), 4);
+  L.pinv = o;    o += MSVIT_MAX_EIG_BLOCK;
+  L.misc = o;    o += 8 + 3 * MSVIT_MAX_EIG_BLOCK;
+  L.colred = o;  o += nwarps * MSVIT_MAX_EIG_BLOCK;
+  L.jac = o;     o += 4 * m * m;                      // Jacobi ping-pong: H[2][m*m], S[2][m*m]
+  L.ptab = o;    o += (m * m + 3) / 4;                // round-robin partner table, (m-1) x m bytes
   L.total = o;
   return L;
 }
@@ -79,96 +89,165 @@ __device__ __forceinline__ float hash_unit(uint32_t i, uint32_t c) {
   return static_cast<float>(static_cast<int32_t>(h)) * (1.0f / 2147483648.0f);
 }
 
-// Y = D^-1 (A U).  A symmetric: the 4 output rows 4rg..4rg+3 read A[j][4rg..4rg+3] (one 16-byte load per j).
-template <bool RESIDENT>
-__device__ __forceinline__ void matvec(const float* __restrict__ A, int lda, int n, int m,
-                                       const float* __restrict__ Us, float* __restrict__ Ys,
-                                       const float* __restrict__ dg) {
-  const int CG = m >> 2;
-  const int tiles = ((n + 3) >> 2) * CG;
-  for (int tile = threadIdx.x; tile < tiles; tile += kThreads) {
-    const int rg = tile / CG, cg = tile - rg * CG;
-    float acc[4][4];
+// ----------------------------------------------------------------------------- tensor-core pieces
+// D += A(16x8, row) * B(8x8, col), TF32 operands (low 13 mantissa bits ignored), fp32 accumulate.
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// x = hi + lo exactly: hi = x truncated to TF32 (what the tensor core reads from x's bits), lo = the remainder.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void split4(const float4& v, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+  split_tf32(v.x, hi[0], lo[0]);
+  split_tf32(v.y, hi[1], lo[1]);
+  split_tf32(v.z, hi[2], lo[2]);
+  split_tf32(v.w, hi[3], lo[3]);
+}
+
+// One 16-column block of  acc += [e; f] * b^T : e, f = 4 consecutive columns of rows g, g+8 of the left operand,
+// b = the same 4 columns of row g of the (transposed) right operand.  Inside the block the MMA's k index is
+// permuted (lane t covers columns 4t..4t+3 as k = t, t+4 of two k-steps), identically for both operands.
+template <bool FULL>
+__device__ __forceinline__ void mma_block(float (&hi)[4], float (&lo)[4], const uint32_t (&eh)[4],
+                                          const uint32_t (&el)[4], const uint32_t (&fh)[4], const uint32_t (&fl)[4],
+                                          const uint32_t (&bh)[4], const uint32_t (&bl)[4]) {
+  if constexpr (FULL) {
+    mma_tf32(lo, el[0], fl[0], el[1], fl[1], bh[0], bh[1]);
+    mma_tf32(lo, eh[0], fh[0], eh[1], fh[1], bl[0], bl[1]);
+    mma_tf32(lo, el[2], fl[2], el[3], fl[3], bh[2], bh[3]);
+    mma_tf32(lo, eh[2], fh[2], eh[3], fh[3], bl[2], bl[3]);
+  }
+  mma_tf32(hi, eh[0], fh[0], eh[1], fh[1], bh[0], bh[1]);
+  mma_tf32(hi, eh[2], fh[2], eh[3], fh[3], bh[2], bh[3]);
+}
+
+// Y^T[c][i] = dinv[i] * sum_j A[i][j] U^T[c][j].  One warp per 16 rows of A; the affinity block is read straight
+// from global memory (L2), two 16-column blocks in flight per lane.
+template <int NT, bool FULL>
+__device__ __forceinline__ void matvec(const float* __restrict__ Ag, int lda, int n, const float* __restrict__ Ut,
+                                       float* __restrict__ Yt, const float* __restrict__ dinv, int ldt, int nwarps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int KB = (n + 15) >> 4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tile = warp; tile < KB; tile += nwarps) {
+    const int r0 = 16 * tile + g, r1 = r0 + 8;
+    const bool v0 = r0 < n, v1 = r1 < n;
+    const float* p0 = Ag + static_cast<size_t>(v0 ? r0 : 0) * lda + 4 * t;
+    const float* p1 = Ag + static_cast<size_t>(v1 ? r1 : 0) * lda + 4 * t;
+    const float* up = Ut + g * ldt + 4 * t;
+    float hi[NT][4], lo[NT][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-    const float* ap = A + 4 * rg;
-    const float* up = Us + 4 * cg;
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) {
-      float4 a;
-      if constexpr (RESIDENT) a = *reinterpret_cast<const float4*>(ap + static_cast<size_t>(j) * lda);
-      else a = __ldg(reinterpret_cast<const float4*>(ap + static_cast<size_t>(j) * lda));
-      const float4 u = *reinterpret_cast<const float4*>(up + j * m);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float uv[4] = {u.x, u.y, u.z, u.w};
+      for (int q = 0; q < 4; ++q) hi[nt][q] = lo[nt][q] = 0.f;
+    const int cmax = lda - 4 * t;  // column block kb is in range iff 16 * kb < cmax
+    float4 e0 = (v0 && 0 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0)) : zero4;
+    float4 f0 = (v1 && 0 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1)) : zero4;
+    float4 e1 = (v0 && 16 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0 + 16)) : zero4;
+    float4 f1 = (v1 && 16 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1 + 16)) : zero4;
+    for (int kb = 0; kb < KB; kb += 2) {
+      const float4 ce0 = e0, cf0 = f0, ce1 = e1, cf1 = f1;
+      const int c2 = 16 * (kb + 2), c3 = c2 + 16;
+      e0 = (v0 && c2 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0 + c2)) : zero4;
+      f0 = (v1 && c2 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1 + c2)) : zero4;
+      e1 = (v0 && c3 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0 + c3)) : zero4;
+      f1 = (v1 && c3 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1 + c3)) : zero4;
+      {
+        uint32_t eh[4], el[4], fh[4], fl[4];
+        split4(ce0, eh, el);
+        split4(cf0, fh, fl);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int nt = 0; nt < NT; ++nt) {
+          const float4 u = *reinterpret_cast<const float4*>(up + 8 * nt * ldt + 16 * kb);
+          uint32_t uh[4], ul[4];
+          split4(u, uh, ul);
+          mma_block<FULL>(hi[nt], lo[nt], eh, el, fh, fl, uh, ul);
+        }
+      }
+      if (kb + 1 < KB) {
+        uint32_t eh[4], el[4], fh[4], fl[4];
+        split4(ce1, eh, el);
+        split4(cf1, fh, fl);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], uv[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int row = 4 * rg + r;
-      if (row < n) {
-        const float inv = 1.0f / dg[row];
-        *reinterpret_cast<float4*>(Ys + row * m + 4 * cg) =
-            make_float4(acc[r][0] * inv, acc[r][1] * inv, acc[r][2] * inv, acc[r][3] * inv);
+        for (int nt = 0; nt < NT; ++nt) {
+          const float4 u = *reinterpret_cast<const float4*>(up + 8 * nt * ldt + 16 * (kb + 1));
+          uint32_t uh[4], ul[4];
+          split4(u, uh, ul);
+          mma_block<FULL>(hi[nt], lo[nt], eh, el, fh, fl, uh, ul);
+        }
       }
     }
-  }
-}
-
-// Out[a][b] = sum_i dg[i] * P[i][a] * Q[i][b]   (m x m, row stride m + 1).
-// 4x4 blocks of the result x row slices; partials go through `scratch` and are summed in a fixed order.
-__device__ __forceinline__ void weighted_gram(const float* __restrict__ Ps, const float* __restrict__ Qs,
-                                              const float* __restrict__ dg, int n, int m, float* __restrict__ Out,
-                                              float* __restrict__ scratch) {
-  const int CG = m >> 2;
-  const int blocks = CG * CG;
-  int slices = kThreads / blocks;
-  if (slices < 1) slices = 1;
-  if (slices * m * m > kScratchFloats) slices = kScratchFloats / (m * m);
-  for (int w = threadIdx.x; w < blocks * slices; w += kThreads) {
-    const int blk = w % blocks, sl = w / blocks;
-    const int a0 = (blk / CG) * 4, b0 = (blk % CG) * 4;
-    float acc[4][4];
+    const float d0 = v0 ? dinv[r0] : 0.f, d1 = v1 ? dinv[r1] : 0.f;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-    for (int i = sl; i < n; i += slices) {
-      const float d = dg[i];
-      const float4 p = *reinterpret_cast<const float4*>(Ps + i * m + a0);
-      const float4 q = *reinterpret_cast<const float4*>(Qs + i * m + b0);
-      const float pv[4] = {p.x * d, p.y * d, p.z * d, p.w * d};
-      const float qv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(pv[r], qv[c], acc[r][c]);
+    for (int nt = 0; nt < NT; ++nt) {
+      float* y = Yt + (8 * nt + 2 * t) * ldt;
+      y[r0] = (hi[nt][0] + lo[nt][0]) * d0;
+      y[ldt + r0] = (hi[nt][1] + lo[nt][1]) * d0;
+      y[r1] = (hi[nt][2] + lo[nt][2]) * d1;
+      y[ldt + r1] = (hi[nt][3] + lo[nt][3]) * d1;
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) scratch[sl * m * m + (a0 + r) * m + b0 + c] = acc[r][c];
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < m * m; e += kThreads) {
-    float s = 0.f;
-    for (int sl = 0; sl < slices; ++sl) s += scratch[sl * m * m + e];
-    Out[(e / m) * (m + 1) + (e % m)] = s;
+}
+
+// G[a][c] = sum_i dg[i] Q^T[a][i] Q^T[c][i]   and   H[a][c] = sum_i dg[i] P^T[a][i] Q^T[c][i]   (m x m, row
+// stride m + 1).  One warp per 16 x 8 output tile, the whole token range per warp: no cross-warp reduction.
+__device__ __forceinline__ void weighted_grams(const float* __restrict__ Pt, const float* __restrict__ Qt,
+                                               const float* __restrict__ dg, int n, int m, int ldt,
+                                               float* __restrict__ Gs, float* __restrict__ Hs, bool want_h,
+                                               int nwarps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int KB = (n + 15) >> 4;
+  const int MT = (m + 15) >> 4, NTg = (m + 7) >> 3;
+  const int per = MT * NTg;
+  const int ntiles = want_h ? 2 * per : per;
+  const int ld = m + 1;
+  for (int tile = warp; tile < ntiles; tile += nwarps) {
+    const int mat = tile / per, rem = tile - mat * per;
+    const int mt = rem / NTg, nt = rem - mt * NTg;
+    const float* at = (mat == 0 ? Qt : Pt) + (16 * mt + g) * ldt + 4 * t;
+    const float* bt = Qt + (8 * nt + g) * ldt + 4 * t;
+    const float* dp = dg + 4 * t;
+    float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int kb = 0; kb < KB; ++kb) {
+      const float4 a0 = *reinterpret_cast<const float4*>(at + 16 * kb);
+      const float4 a1 = *reinterpret_cast<const float4*>(at + 8 * ldt + 16 * kb);
+      float4 b = *reinterpret_cast<const float4*>(bt + 16 * kb);
+      const float4 d = *reinterpret_cast<const float4*>(dp + 16 * kb);
+      b.x *= d.x; b.y *= d.y; b.z *= d.z; b.w *= d.w;
+      uint32_t eh[4], el[4], fh[4], fl[4], bh[4], bl[4];
+      split4(a0, eh, el);
+      split4(a1, fh, fl);
+      split4(b, bh, bl);
+      mma_block<true>(hi, lo, eh, el, fh, fl, bh, bl);
+    }
+    float* out = mat == 0 ? Gs : Hs;
+    const int r0 = 16 * mt + g, r1 = r0 + 8, c0 = 8 * nt + 2 * t, c1 = c0 + 1;
+    if (r0 < m && c0 < m) out[r0 * ld + c0] = hi[0] + lo[0];
+    if (r0 < m && c1 < m) out[r0 * ld + c1] = hi[1] + lo[1];
+    if (r1 < m && c0 < m) out[r1 * ld + c0] = hi[2] + lo[2];
+    if (r1 < m && c1 < m) out[r1 * ld + c1] = hi[3] + lo[3];
   }
   __syncthreads();
 }
 
+// ----------------------------------------------------------------------------- small dense pieces
 // In-place Cholesky of the leading me x me block of G (row stride m + 1) by warp 0: lane i keeps row i in
-// registers, row j is broadcast by shuffles (left-looking), L is written back to the lower triangle.
-// Returns (to every thread) the smallest pivot of the unit-diagonal-scaled matrix, i.e. a conditioning
-// estimate that ignores column scaling.  Non-positive pivots zero the column (rank deficiency).
+// registers, row j is broadcast by shuffles (left-looking), L is written back to the lower triangle and the
+// reciprocal pivots to pinv (0 for a dropped column).  Returns (to every thread) the smallest pivot of the
+// unit-diagonal-scaled matrix, i.e. a conditioning estimate that ignores column scaling.
 template <int MB>
-__device__ __forceinline__ float cholesky(float* __restrict__ G, int m, int me, float* __restrict__ misc) {
+__device__ __forceinline__ float cholesky(float* __restrict__ G, int m, int me, float* __restrict__ pinv,
+                                          float* __restrict__ misc) {
   const int ld = m + 1;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
@@ -197,6 +276,7 @@ __device__ __forceinline__ float cholesky(float* __restrict__ G, int m, int me, 
         const float ljj = ok ? sqrtf(piv) : 0.f;
         const float inv = ok ? 1.0f / ljj : 0.f;
         g[j] = lane == j ? ljj : (lane > j ? s * inv : 0.f);
+        if (lane == j) pinv[j] = inv;
       }
     }
     if (lane < me) {
@@ -210,28 +290,32 @@ __device__ __forceinline__ float cholesky(float* __restrict__ G, int m, int me, 
   return misc[0];
 }
 
-// X <- X L^-T  row by row (forward substitution), L from `cholesky`.  Columns with a zero pivot become 0.
+// X^T <- (Y L^-T)^T token by token (forward substitution), L from `cholesky`.  Columns with a zero pivot and
+// the pad tokens n .. npad-1 become 0.
 template <int MB>
-__device__ __forceinline__ void trisolve_rows(float* __restrict__ Xs, const float* __restrict__ Ys, int n, int m,
-                                              int me, const float* __restrict__ L) {
-  const int ld = m + 1;
-  for (int i = threadIdx.x; i < n; i += kThreads) {
+__device__ __forceinline__ void trisolve(float* __restrict__ Xt, const float* __restrict__ Yt, int n, int npad,
+                                         int me, int ldt, const float* __restrict__ L, int ld,
+                                         const float* __restrict__ pinv) {
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
     float y[MB];
 #pragma unroll
-    for (int c = 0; c < MB; ++c) y[c] = c < me ? Ys[i * m + c] : 0.f;
+    for (int c = 0; c < MB; ++c) y[c] = (c < me && i < n) ? Yt[c * ldt + i] : 0.f;
 #pragma unroll
     for (int c = 0; c < MB; ++c) {
       if (c < me) {
-        float t = y[c];
+        float s0 = y[c], s1 = 0.f;
 #pragma unroll
-        for (int k2 = 0; k2 < c; ++k2) t = fmaf(-y[k2], L[c * ld + k2], t);
-        const float piv = L[c * ld + c];
-        y[c] = piv > 0.f ? t / piv : 0.f;
+        for (int a = 0; a + 1 < c; a += 2) {
+          s0 = fmaf(-y[a], L[c * ld + a], s0);
+          s1 = fmaf(-y[a + 1], L[c * ld + a + 1], s1);
+        }
+        if (c & 1) s0 = fmaf(-y[c - 1], L[c * ld + c - 1], s0);
+        y[c] = (s0 + s1) * pinv[c];
       }
     }
 #pragma unroll
     for (int c = 0; c < MB; ++c)
-      if (c < m) Xs[i * m + c] = y[c];
+      if (c < me) Xt[c * ldt + i] = y[c];
   }
   __syncthreads();
 }
@@ -269,9 +353,10 @@ __device__ __forceinline__ void jacobi_rot(float app, float aqq, float apq, floa
 __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int m, float* __restrict__ jac,
                                        const uint8_t* __restrict__ ptab) {
   const int ld = m + 1, mm = m * m;
+  const int nthreads = blockDim.x;
   float* JH = jac;           // [2][mm]
   float* JS = jac + 2 * mm;  // [2][mm]
-  for (int e = threadIdx.x; e < mm; e += kThreads) {
+  for (int e = threadIdx.x; e < mm; e += nthreads) {
     const int a = e / m, b = e - a * m;
     JH[e] = 0.5f * (H[a * ld + b] + H[b * ld + a]);
     JS[e] = a == b ? 1.f : 0.f;
@@ -285,7 +370,7 @@ __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict_
       const float* __restrict__ sin_ = JS + cur * mm;
       float* __restrict__ hout = JH + (cur ^ 1) * mm;
       float* __restrict__ sout = JS + (cur ^ 1) * mm;
-      for (int e = threadIdx.x; e < mm; e += kThreads) {
+      for (int e = threadIdx.x; e < mm; e += nthreads) {
         const int a = e / m, b = e - a * m;
         const int pa = ptab[r * m + a], pb = ptab[r * m + b];
         const int p1 = min(a, pa), q1 = max(a, pa), p2 = min(b, pb), q2 = max(b, pb);
@@ -300,13 +385,13 @@ __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict_
         sout[e] = fmaf(g2, sin_[a * m + pb], c2 * sin_[e]);
       }
       cur ^= 1;
-      if (r < m - 2) __syncthreads();
+      __syncthreads();
     }
     if (!__syncthreads_or(big ? 1 : 0)) break;
   }
   const float* __restrict__ hf = JH + cur * mm;
   const float* __restrict__ sf = JS + cur * mm;
-  for (int e = threadIdx.x; e < mm; e += kThreads) {
+  for (int e = threadIdx.x; e < mm; e += nthreads) {
     const int a = e / m, b = e - a * m;
     H[a * ld + b] = hf[e];
     Sm[a * ld + b] = sf[e];
@@ -314,56 +399,58 @@ __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict_
   __syncthreads();
 }
 
-// Residuals of the leading columns against span(U) or against their Ritz values, reduced per column:
-// out[c] = sum_i dg[i] * r_ic^2.  Warp shuffle reduction, then a fixed-order sum over warps (deterministic).
+// Per-column sums of per-thread partials: out[c] = sum over threads of rloc[c].  Warp shuffle reduction, then a
+// fixed-order sum over warps (deterministic).
 template <int MB>
-__device__ __forceinline__ void reduce_columns(const float (&rloc)[MB], int ncols, float* __restrict__ scratch,
+__device__ __forceinline__ void reduce_columns(const float (&rloc)[MB], int ncols, float* __restrict__ colred,
                                                float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int c = 0; c < MB; ++c) {
     if (c < ncols) {
       const float v = warp_sum(rloc[c]);
-      if (lane == 0) scratch[warp * MSVIT_MAX_EIG_BLOCK + c] = v;
+      if (lane == 0) colred[warp * MSVIT_MAX_EIG_BLOCK + c] = v;
     }
   }
   __syncthreads();
   if (threadIdx.x < ncols) {
     float v = 0.f;
-    for (int w = 0; w < kWarps; ++w) v += scratch[w * MSVIT_MAX_EIG_BLOCK + threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) v += colred[w * MSVIT_MAX_EIG_BLOCK + threadIdx.x];
     out[threadIdx.x] = v;
   }
   __syncthreads();
 }
 
-template <int MB, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const Params P) {
+// NT: 8-column tiles of the block (m <= 8 * NT).  THREADS: CTA size.
+template <int NT, int THREADS>
+__global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS) : 1) ncut_eig_kernel(const Params P) {
+  constexpr int MB = 8 * NT;
+  constexpr int ROWS = NT > 2 ? 32 : 16;
+  constexpr int NWARPS = THREADS / 32;
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t load_bar;
-  const Layout L = make_layout(P.N, P.m, RESIDENT);
-  float* As = smem + L.As;
-  float* Us = smem + L.Us;
-  float* Ys = smem + L.Ys;
-  float* Gs = smem + L.Gs;
-  float* Ss = smem + L.Ss;
+  const Layout L = make_layout(P.N, P.m, ROWS, NWARPS);
+  float* Ut = smem + L.Ut;
+  float* Yt = smem + L.Yt;
   float* dg = smem + L.dg;
-  float* scratch = smem + L.scratch;
+  float* dinv = smem + L.dinv;
+  float* Gs = smem + L.Gs;
+  float* Hs = smem + L.Hs;
+  float* Ss = smem + L.Ss;
+  float* pinv = smem + L.pinv;
   float* misc = smem + L.misc;           // [0] = scalar broadcast, [1] = worst residual, [2] = trigger flag
   float* theta = misc + 8;               // [m] Ritz values in sorted order
   float* res = theta + MSVIT_MAX_EIG_BLOCK;   // [m] squared residuals / column signs
   int* order = reinterpret_cast<int*>(res + MSVIT_MAX_EIG_BLOCK);  // [m] sorted position -> Jacobi column
+  float* colred = smem + L.colred;
   float* jac = smem + L.jac;
   uint8_t* ptab = reinterpret_cast<uint8_t*>(smem + L.ptab);
+  const int ldt = L.ldt;
 
   const int m = P.m, k = P.k;
+  const int ld = m + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(&load_bar, 1);
-    fence_mbar_init();
-  }
-  for (int e = threadIdx.x; e < (m - 1) * m; e += kThreads) ptab[e] = static_cast<uint8_t>(rr_partner(e % m, e / m, m));
-  __syncthreads();
-  uint32_t load_phase = 0;
+  for (int e = threadIdx.x; e < (m - 1) * m; e += THREADS) ptab[e] = static_cast<uint8_t>(rr_partner(e % m, e / m, m));
 
   for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
     const Seg g = seg_info(s, P.N, P.seg_off, P.a_off);
@@ -371,102 +458,95 @@ __global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const
     float* __restrict__ Vout = P.V + static_cast<long long>(g.row0) * k;
     float* __restrict__ lout = P.lam + static_cast<long long>(s) * k;
     if (n <= 0) {
-      for (int c = threadIdx.x; c < k; c += kThreads) lout[c] = 0.f;
+      for (int c = threadIdx.x; c < k; c += THREADS) lout[c] = 0.f;
       if (P.iters && threadIdx.x == 0) P.iters[s] = 0;
       continue;
     }
     const float* Ag = P.A + g.a0;
     const int lda = g.lda;
-    const int me = n < m ? n : m;  // effective block width
+    const int me = n < m ? n : m;    // effective block width
     const int kk = k < me ? k : me;  // wanted pairs that exist
+    const int npad = ((n + 15) >> 4) << 4;
 
-    // ---- load: affinity block (bulk async copy), degree, start block
-    if constexpr (RESIDENT) {
-      if (threadIdx.x == 0) {
-        fence_proxy_async_smem();  // earlier generic-proxy reads of As are ordered before the async writes
-        const uint32_t total = static_cast<uint32_t>(n) * lda * 4u;
-        mbar_arrive_expect_tx(&load_bar, total);
-        for (uint32_t off = 0; off < total; off += 32768u) {
-          const uint32_t len = total - off < 32768u ? total - off : 32768u;
-          bulk_load_1d(reinterpret_cast<uint8_t*>(As) + off, reinterpret_cast<const uint8_t*>(Ag) + off, len,
-                       &load_bar);
-        }
-      }
+    // ---- load: degree, start block (pad tokens and pad columns are zero)
+    __syncthreads();  // the previous segment's readers of the shared arrays are done
+    for (int i = threadIdx.x; i < npad; i += THREADS) {
+      const float d = i < n ? P.deg[g.row0 + i] : 0.f;
+      dg[i] = d;
+      dinv[i] = d > 0.f ? 1.0f / d : 0.f;
     }
-    for (int i = threadIdx.x; i < n; i += kThreads) dg[i] = P.deg[g.row0 + i];
-    for (int e = threadIdx.x; e < n * m; e += kThreads) {
-      const int i = e / m, c = e - i * m;
-      float v;
-      if (n <= m) v = (i == c) ? 1.f : 0.f;
-      else v = (c == 0) ? 1.f : hash_unit(i, c);
-      Us[e] = c < me ? v : 0.f;
+    for (int e = threadIdx.x; e < ROWS * npad; e += THREADS) {
+      const int c = e / npad, i = e - c * npad;
+      float v = 0.f;
+      if (c < me && i < n) {
+        if (n <= m) v = (i == c) ? 1.f : 0.f;
+        else v = (c == 0) ? 1.f : hash_unit(i, c);
+      }
+      Ut[c * ldt + i] = v;
+      Yt[c * ldt + i] = 0.f;
     }
     __syncthreads();
 
     // ---- D-orthonormalise the start block
-    weighted_gram(Us, Us, dg, n, m, Gs, scratch);
-    cholesky<MB>(Gs, m, me, misc);
-    trisolve_rows<MB>(Us, Us, n, m, me, Gs);
-
-    if constexpr (RESIDENT) {
-      mbar_wait(&load_bar, load_phase);
-      load_phase ^= 1;
-    }
-    const float* Amat = RESIDENT ? As : Ag;
+    weighted_grams(Ut, Ut, dg, n, m, ldt, Gs, Hs, false, NWARPS);
+    cholesky<MB>(Gs, m, me, pinv, misc);
+    trisolve<MB>(Ut, Ut, n, npad, me, ldt, Gs, ld, pinv);
 
     int it = 0;
     const float tol2 = P.tol * P.tol;
     while (true) {
       ++it;
-      matvec<RESIDENT>(Amat, lda, n, m, Us, Ys, dg);
+      if (it <= P.fast_iters) matvec<NT, false>(Ag, lda, n, Ut, Yt, dinv, ldt, NWARPS);
+      else matvec<NT, true>(Ag, lda, n, Ut, Yt, dinv, ldt, NWARPS);
       __syncthreads();
       const bool last = it >= P.max_iter || n <= m;  // n <= m: span(U) is the whole space, one step is exact
-      // ---- H = U^T D Y (U is D-orthonormal) and the trigger: for each wanted column j
+      // ---- G = Y^T D Y, H = U^T D Y (U is D-orthonormal) and the trigger: for each wanted column j
       //        |y_j - U h_j|_D^2 + sum_{a >= kk} H[a][j]^2   =   residual of the Ritz problem on the leading columns
-      weighted_gram(Us, Ys, dg, n, m, Gs, scratch);
+      weighted_grams(Ut, Yt, dg, n, m, ldt, Gs, Hs, true, NWARPS);
       bool do_rr = last || (it % P.rr_every) == 0;
-      if (!do_rr && it >= 2) {
+      if (!do_rr && it >= 2 && it > P.fast_iters) {
         float rloc[MB];
 #pragma unroll
         for (int c = 0; c < MB; ++c) rloc[c] = 0.f;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
+        for (int i = threadIdx.x; i < n; i += THREADS) {
           float u[MB];
 #pragma unroll
-          for (int a = 0; a < MB; ++a) u[a] = a < m ? Us[i * m + a] : 0.f;
+          for (int a = 0; a < MB; ++a) u[a] = a < m ? Ut[a * ldt + i] : 0.f;
           const float d = dg[i];
 #pragma unroll
           for (int c = 0; c < MB; ++c) {
             if (c < kk) {
-              float r = Ys[i * m + c];
+              float r = Yt[c * ldt + i];
 #pragma unroll
               for (int a = 0; a < MB; ++a)
-                if (a < m) r = fmaf(-u[a], Gs[a * (m + 1) + c], r);
+                if (a < m) r = fmaf(-u[a], Hs[a * ld + c], r);
               rloc[c] = fmaf(d * r, r, rloc[c]);
             }
           }
         }
-        reduce_columns<MB>(rloc, kk, scratch, res);
+        reduce_columns<MB>(rloc, kk, colred, res);
         if (threadIdx.x == 0) {
           float worst = 0.f;
           for (int c = 0; c < kk; ++c) {
             float v = res[c];
-            for (int a = kk; a < me; ++a) v = fmaf(Gs[a * (m + 1) + c], Gs[a * (m + 1) + c], v);
-            if (Gs[c * (m + 1) + c] >= P.lam_floor) worst = fmaxf(worst, v);
+            for (int a = kk; a < me; ++a) v = fmaf(Hs[a * ld + c], Hs[a * ld + c], v);
+            if (Hs[c * ld + c] >= P.lam_floor) worst = fmaxf(worst, v);
           }
           misc[2] = worst <= tol2 ? 1.f : 0.f;
         }
         __syncthreads();
         do_rr = misc[2] != 0.f;
       }
+      bool rotated = false;
       if (do_rr) {
         // ---- Rayleigh-Ritz on span(U)
-        jacobi(Gs, Ss, m, jac, ptab);
+        jacobi(Hs, Ss, m, jac, ptab);
         if (threadIdx.x < m) {
           const int a = threadIdx.x;
-          const float ta = Gs[a * (m + 1) + a];
+          const float ta = Hs[a * ld + a];
           int rank = 0;
           for (int b = 0; b < m; ++b) {
-            const float tb = Gs[b * (m + 1) + b];
+            const float tb = Hs[b * ld + b];
             rank += (tb > ta || (tb == ta && b < a)) ? 1 : 0;
           }
           order[rank] = a;
@@ -477,12 +557,12 @@ __global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const
         float rloc[MB];
 #pragma unroll
         for (int c = 0; c < MB; ++c) rloc[c] = 0.f;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
+        for (int i = threadIdx.x; i < n; i += THREADS) {
           float u[MB], y[MB];
 #pragma unroll
           for (int c = 0; c < MB; ++c) {
-            u[c] = c < m ? Us[i * m + c] : 0.f;
-            y[c] = c < m ? Ys[i * m + c] : 0.f;
+            u[c] = c < m ? Ut[c * ldt + i] : 0.f;
+            y[c] = c < m ? Yt[c * ldt + i] : 0.f;
           }
           const float d = dg[i];
 #pragma unroll
@@ -493,19 +573,19 @@ __global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const
 #pragma unroll
               for (int a = 0; a < MB; ++a) {
                 if (a < m) {
-                  const float sv = Ss[a * (m + 1) + col];
+                  const float sv = Ss[a * ld + col];
                   nu = fmaf(u[a], sv, nu);
                   ny = fmaf(y[a], sv, ny);
                 }
               }
-              Us[i * m + c] = nu;
-              Ys[i * m + c] = ny;
+              Ut[c * ldt + i] = nu;
+              Yt[c * ldt + i] = ny;
               const float rr = ny - theta[c] * nu;
               rloc[c] = fmaf(d * rr, rr, rloc[c]);
             }
           }
         }
-        reduce_columns<MB>(rloc, kk, scratch, res);
+        reduce_columns<MB>(rloc, kk, colred, res);
         if (threadIdx.x == 0) {
           float worst = 0.f;
           for (int c = 0; c < kk; ++c)
@@ -514,26 +594,27 @@ __global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const
         }
         __syncthreads();
         if (last || misc[1] <= tol2) break;
+        rotated = true;
       }
       // ---- U = orth_D(Y)
-      weighted_gram(Ys, Ys, dg, n, m, Gs, scratch);
-      const float piv = cholesky<MB>(Gs, m, me, misc);
-      trisolve_rows<MB>(Us, Ys, n, m, me, Gs);
+      if (rotated) weighted_grams(Ut, Yt, dg, n, m, ldt, Gs, Hs, false, NWARPS);  // G of the rotated Y
+      const float piv = cholesky<MB>(Gs, m, me, pinv, misc);
+      trisolve<MB>(Ut, Yt, n, npad, me, ldt, Gs, ld, pinv);
       if (piv < 0.05f) {
-        weighted_gram(Us, Us, dg, n, m, Gs, scratch);
-        cholesky<MB>(Gs, m, me, misc);
-        trisolve_rows<MB>(Us, Us, n, m, me, Gs);
+        weighted_grams(Ut, Ut, dg, n, m, ldt, Gs, Hs, false, NWARPS);
+        cholesky<MB>(Gs, m, me, pinv, misc);
+        trisolve<MB>(Ut, Ut, n, npad, me, ldt, Gs, ld, pinv);
       }
     }
 
     // ---- output: v = sqrt(d) * u, canonical sign, eigenvalues
-    for (int c = warp; c < k; c += kWarps) {
+    for (int c = warp; c < k; c += NWARPS) {
       float best = -1.f;
       int bidx = 0x7fffffff;
       float bval = 0.f;
       if (c < me) {
         for (int i = lane; i < n; i += 32) {
-          const float v = Us[i * m + c] * sqrtf(dg[i]);
+          const float v = Ut[c * ldt + i] * sqrtf(dg[i]);
           const float av = fabsf(v);
           if (av > best) { best = av; bidx = i; bval = v; }
         }
@@ -551,30 +632,39 @@ __global__ void __launch_bounds__(kThreads, EIG_MINBLOCKS) ncut_eig_kernel(const
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n * k; e += kThreads) {
+    for (int e = threadIdx.x; e < n * k; e += THREADS) {
       const int i = e / k, c = e - i * k;
-      Vout[e] = c < me ? Us[i * m + c] * sqrtf(dg[i]) * res[c] : 0.f;
+      Vout[e] = c < me ? Ut[c * ldt + i] * sqrtf(dg[i]) * res[c] : 0.f;
     }
     if (P.iters && threadIdx.x == 0) P.iters[s] = it;
-    __syncthreads();
   }
 }
 
-template <int MB>
-static int launch(const Params& P, int grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e;
-  if (P.a_resident) {
-    e = cudaFuncSetAttribute(ncut_eig_kernel<MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
-    if (e != cudaSuccess) return cuda_status(e);
-    ncut_eig_kernel<MB, true><<<grid, kThreads, smem, stream>>>(P);
-  } else {
-    e = cudaFuncSetAttribute(ncut_eig_kernel<MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
-    if (e != cudaSuccess) return cuda_status(e);
-    ncut_eig_kernel<MB, false><<<grid, kThreads, smem, stream>>>(P);
-  }
+template <int NT, int THREADS>
+static int launch(const Params& P, cudaStream_t stream) {
+  constexpr int ROWS = NT > 2 ? 32 : 16;
+  const size_t smem = static_cast<size_t>(make_layout(P.N, P.m, ROWS, THREADS / 32).total) * 4;
+  const size_t kMaxSmem = 227 * 1024;
+  if (smem > kMaxSmem) return MSVIT_ERR_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(ncut_eig_kernel<NT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_status(e);
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncut_eig_kernel<NT, THREADS>, THREADS, smem);
+  if (e != cudaSuccess) return cuda_status(e);
+  if (per_sm < 1) per_sm = 1;
+  // one CTA per segment while that is at most a few waves, else a persistent grid-stride loop
+  const long long cap = 16LL * per_sm * sm_count();
+  const int grid = static_cast<int>(P.S < cap ? P.S : cap);
+  ncut_eig_kernel<NT, THREADS><<<grid, THREADS, smem, stream>>>(P);
   return cuda_status(cudaGetLastError());
+}
+
+template <int NT>
+static int launch_threads(const Params& P, cudaStream_t stream) {
+  if (P.N <= 256) return launch<NT, 128>(P, stream);
+  if (P.N <= 512) return launch<NT, 256>(P, stream);
+  return launch<NT, 512>(P, stream);
 }
 
 }  // namespace eig
@@ -593,20 +683,13 @@ extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float*
   if (S == 0 || total_rows == 0) return MSVIT_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-  const size_t kMaxSmem = 227 * 1024 - 64;  // static mbarrier lives in the same budget
   Params P;
   P.A = A; P.deg = deg; P.V = V; P.lam = lam; P.iters = iters;
   P.seg_off = seg_off; P.a_off = a_off;
   P.S = S; P.N = N; P.k = k; P.m = block;
   P.max_iter = max_iter; P.rr_every = 3; P.tol = tol; P.lam_floor = lam_floor;
-  size_t smem = static_cast<size_t>(make_layout(N, block, true).total) * 4;
-  P.a_resident = smem <= kMaxSmem ? 1 : 0;
-#ifdef EIG_FORCE_STREAM
-  P.a_resident = 0;
-#endif
-  if (!P.a_resident) smem = static_cast<size_t>(make_layout(N, block, false).total) * 4;
-  if (smem > kMaxSmem) return MSVIT_ERR_SHAPE;
-  const int grid = S < 8 * sm_count() ? S : 8 * sm_count();
-  if (block <= 16) return launch<16>(P, grid, smem, stream);
-  return launch<32>(P, grid, smem, stream);
+  P.fast_iters = 0;
+  if (block <= 16) return launch_threads<2>(P, stream);
+  if (block <= 24) return launch_threads<3>(P, stream);
+  return launch_threads<4>(P, stream);
 }
