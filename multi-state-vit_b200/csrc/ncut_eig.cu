@@ -8,26 +8,29 @@
 // The iteration runs in the "random walk" coordinates u = D^-1/2 v:
 //     Abar v = lam v   <=>   D^-1 A u = lam u,      v-orthonormal  <=>  u^T D u = I
 // so the affinity is used exactly as stored (no scaled copy).  The n x m blocks U and Y live in shared
-// memory TRANSPOSED (row c = column c of the block, row stride ldt with ldt % 32 == 16, so that the
-// 128-bit fragment loads below are bank-conflict free); the affinity block itself is streamed from
-// global memory / L2 once per iteration, which keeps the CTA small enough (~37 KB, 128 threads at
-// N = 196) for several segments to be in flight per SM: the serial m x m steps of one segment
-// (Cholesky, Jacobi) overlap the tensor-core products of the others.
+// memory TRANSPOSED (row c = column c of the block, row stride ldt with ldt % 32 == 16, so that 128-bit
+// fragment loads are bank-conflict free), U additionally in MMA fragment order; the affinity block itself
+// is streamed from global memory / L2 once per iteration, which keeps the CTA small (~50 KB, 128 threads at
+// N = 196) so that several segments are in flight per SM: the serial m x m steps of one segment (Cholesky,
+// Jacobi) overlap the tensor-core products of the others.
 //
-// Per iteration:
-//     Y = D^-1 (A U)             warp-level tensor-core MMA (mma.sync m16n8k8, TF32 operands, fp32 accumulate)
-//                                with the 3-product split  a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (a_hi = a
-//                                truncated to TF32, a_lo = a - a_hi exactly), i.e. fp32-level accuracy.
-//                                A fragments are 128-bit loads of 4 consecutive columns per lane: the k index
-//                                inside a 16-column block is permuted identically for both operands.
-//     G = Y^T D Y,  H = U^T D Y  same MMA scheme, one warp per 16 x 8 output tile
+// All n-sized products run on the tensor cores (mma.sync m16n8k8, TF32 operands, fp32 accumulate) with the
+// 3-product split  a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (a_hi = a truncated to TF32 -- what the tensor
+// core reads from a's bits --, a_lo = a - a_hi exactly), i.e. fp32-level accuracy.  Per iteration:
+//     Y^T = (U^T A) D^-1         U^T fragments are the 16 x 8 left operand (read from the fragment-order copy
+//                                with 128-bit loads), 8 rows of the symmetric A are the right operand: each lane
+//                                loads 4 consecutive columns (one 128-bit load, two k-steps); the k index inside
+//                                a 16-column block is permuted identically for both operands.
+//     G = Y^T D Y,  H = U^T D Y  one warp per 16 x 8 output tile
 //     trigger                    column residuals |y_j - U h_j|_D of the k leading columns plus their coupling
 //                                to the trailing ones (ordered iteration): fires the Rayleigh-Ritz step
-//     Rayleigh-Ritz (on trigger / every rr_every-th iteration): block-wide parallel-order Jacobi on H (one
-//                                matrix entry per thread, one barrier per round), rotate U and Y, true
-//                                residuals |Abar v - theta v| of the k wanted pairs
-//     U = Y L^-T,  L L^T = G     Cholesky QR in the D inner product (register Cholesky on one warp, rows
-//                                exchanged by shuffles; repeated if ill conditioned)
+//     Rayleigh-Ritz              parallel-order Jacobi (rotations computed once per round, 2 x 2 blocks updated
+//                                in place), then [U; Y] <- W [U; Y] and the true residuals |Abar v - theta v|.
+//                                Scheduled every rr_every-th iteration on the whole m x m H with a few sweeps
+//                                (the span does not change, only its basis); when the trigger fires, on the
+//                                leading block only, to full accuracy.
+//     U^T = L^-1 Y^T, L L^T = G  Cholesky QR in the D inner product (register Cholesky and explicit L^-1 on
+//                                one warp; repeated if ill conditioned)
 // Nothing is atomically accumulated and every reduction has a fixed order: results are bit-reproducible.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -53,8 +56,8 @@ struct Params {
 
 struct Layout {
   // offsets in floats from the dynamic shared memory base
-  int Ut, Yt, dg, dinv, Gs, Hs, Ss, pinv, misc, colred, jac, ptab, total;
-  int ldt;
+  int Ut, Yt, Uf, dg, dinv, Gs, Hs, Ss, Ws, pinv, misc, colred, rot, total;
+  int ldt, rows;
 };
 
 __host__ __device__ inline int ldt_of(int N) {
@@ -62,23 +65,26 @@ __host__ __device__ inline int ldt_of(int N) {
   return (np % 32 == 16) ? np : np + 16;
 }
 
-// rows: 16 or 32 rows of the transposed blocks (>= m, multiple of 16)
-__host__ __device__ inline Layout make_layout(int N, int m, int rows, int nwarps) {
+// MT: 16-row tiles of the transposed blocks (m <= 16 * MT)
+__host__ __device__ inline Layout make_layout(int N, int m, int MT, int nwarps) {
   Layout L;
   L.ldt = ldt_of(N);
+  L.rows = round_up(m, 8);
+  const int mm = round_up(m * (m + 1), 4);
   int o = 0;
-  L.Ut = o;      o += rows * L.ldt;
-  L.Yt = o;      o += rows * L.ldt;
+  L.Ut = o;      o += L.rows * L.ldt;
+  L.Yt = o;      o += L.rows * L.ldt;
+  L.Uf = o;      o += (round_up(N, 16) / 16) * MT * 256;   // U in MMA fragment order (see matvec)
   L.dg = o;      o += round_up(N, 16);
   L.dinv = o;    o += round_up(N, 16);
-  L.Gs = o;      o += round_up(m * (m + 1), 4);
-  L.Hs = o;      o += round_up(m * (m + 1), 4);
-  L.Ss = o;      o += round_up(m * (m + 1), 4);
+  L.Gs = o;      o += mm;
+  L.Hs = o;      o += mm;
+  L.Ss = o;      o += mm;
+  L.Ws = o;      o += mm;
   L.pinv = o;    o += MSVIT_MAX_EIG_BLOCK;
   L.misc = o;    o += 8 + 3 * MSVIT_MAX_EIG_BLOCK;
   L.colred = o;  o += nwarps * MSVIT_MAX_EIG_BLOCK;
-  L.jac = o;     o += 4 * m * m;                      // Jacobi ping-pong: H[2][m*m], S[2][m*m]
-  L.ptab = o;    o += (m * m + 3) / 4;                // round-robin partner table, (m-1) x m bytes
+  L.rot = o;     o += 4 * (MSVIT_MAX_EIG_BLOCK / 2);
   L.total = o;
   return L;
 }
@@ -91,128 +97,135 @@ __device__ __forceinline__ float hash_unit(uint32_t i, uint32_t c) {
 
 // ----------------------------------------------------------------------------- tensor-core pieces
 // D += A(16x8, row) * B(8x8, col), TF32 operands (low 13 mantissa bits ignored), fp32 accumulate.
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1) {
+// Fragments (g = lane / 4, t = lane % 4):  a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);
+// b0 (k = t, n = g)  b1 (k = t+4, n = g);  c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1).
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // x = hi + lo exactly: hi = x truncated to TF32 (what the tensor core reads from x's bits), lo = the remainder.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
+__device__ __forceinline__ uint32_t hi_bits(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t lo_bits(float x) { return __float_as_uint(x - __uint_as_float(hi_bits(x))); }
 __device__ __forceinline__ void split4(const float4& v, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
-  split_tf32(v.x, hi[0], lo[0]);
-  split_tf32(v.y, hi[1], lo[1]);
-  split_tf32(v.z, hi[2], lo[2]);
-  split_tf32(v.w, hi[3], lo[3]);
+  hi[0] = hi_bits(v.x); lo[0] = lo_bits(v.x);
+  hi[1] = hi_bits(v.y); lo[1] = lo_bits(v.y);
+  hi[2] = hi_bits(v.z); lo[2] = lo_bits(v.z);
+  hi[3] = hi_bits(v.w); lo[3] = lo_bits(v.w);
 }
 
-// One 16-column block of  acc += [e; f] * b^T : e, f = 4 consecutive columns of rows g, g+8 of the left operand,
-// b = the same 4 columns of row g of the (transposed) right operand.  Inside the block the MMA's k index is
-// permuted (lane t covers columns 4t..4t+3 as k = t, t+4 of two k-steps), identically for both operands.
-template <bool FULL>
-__device__ __forceinline__ void mma_block(float (&hi)[4], float (&lo)[4], const uint32_t (&eh)[4],
-                                          const uint32_t (&el)[4], const uint32_t (&fh)[4], const uint32_t (&fl)[4],
-                                          const uint32_t (&bh)[4], const uint32_t (&bl)[4]) {
-  if constexpr (FULL) {
-    mma_tf32(lo, el[0], fl[0], el[1], fl[1], bh[0], bh[1]);
-    mma_tf32(lo, eh[0], fh[0], eh[1], fh[1], bl[0], bl[1]);
-    mma_tf32(lo, el[2], fl[2], el[3], fl[3], bh[2], bh[3]);
-    mma_tf32(lo, eh[2], fh[2], eh[3], fh[3], bl[2], bl[3]);
-  }
-  mma_tf32(hi, eh[0], fh[0], eh[1], fh[1], bh[0], bh[1]);
-  mma_tf32(hi, eh[2], fh[2], eh[3], fh[3], bh[2], bh[3]);
-}
+// Fragment-order copy of U^T ("Uf"): for the 16-token block kb, 16-row tile mt and k-step ks, lane (g, t) finds its
+// left-operand fragment as one float4 at  ((kb * MT + mt) * 2 + ks) * 128 + lane * 4:
+//     { U^T[16mt+g][j], U^T[16mt+g+8][j], U^T[16mt+g][j+1], U^T[16mt+g+8][j+1] },   j = 16 kb + 4 t + 2 ks
+// i.e. inside a block the MMA's k index is permuted: k = t <-> token 4t + 2ks, k = t+4 <-> token 4t + 2ks + 1.
+// The matching right operand of 8 rows of A is one 128-bit load per lane: x = A[i0+g][16kb+4t .. +3],
+// (b0, b1) = (x.x, x.y) for ks = 0 and (x.z, x.w) for ks = 1.
 
-// Y^T[c][i] = dinv[i] * sum_j A[i][j] U^T[c][j].  One warp per 16 rows of A; the affinity block is read straight
-// from global memory (L2), two 16-column blocks in flight per lane.
-template <int NT, bool FULL>
-__device__ __forceinline__ void matvec(const float* __restrict__ Ag, int lda, int n, const float* __restrict__ Ut,
-                                       float* __restrict__ Yt, const float* __restrict__ dinv, int ldt, int nwarps) {
+// Y^T[c][i] = dinv[i] * sum_j U^T[c][j] A[i][j]   (A symmetric).  Each warp owns a contiguous range of 8-row tiles of
+// A and works on T of them at a time so that one U fragment load feeds T MMAs; A comes straight from global
+// memory (L2), the next 16-column block is in flight while the current one is multiplied.
+template <int MT, int T, bool FULL, int NWARPS>
+__device__ __forceinline__ void matvec(const float* __restrict__ Ag, int lda, int n, const float* __restrict__ Uf,
+                                       float* __restrict__ Yt, const float* __restrict__ dinv, int ldt, int rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = (n + 15) >> 4;
+  const int ntile = (n + 7) >> 3;
+  const int per = (ntile + NWARPS - 1) / NWARPS;
+  const int tbeg = warp * per;
+  const int tend = min(ntile, tbeg + per);
+  const int cmax = lda - 4 * t;  // column block kb is in range iff 16 * kb < cmax
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int tile = warp; tile < KB; tile += nwarps) {
-    const int r0 = 16 * tile + g, r1 = r0 + 8;
-    const bool v0 = r0 < n, v1 = r1 < n;
-    const float* p0 = Ag + static_cast<size_t>(v0 ? r0 : 0) * lda + 4 * t;
-    const float* p1 = Ag + static_cast<size_t>(v1 ? r1 : 0) * lda + 4 * t;
-    const float* up = Ut + g * ldt + 4 * t;
-    float hi[NT][4], lo[NT][4];
+  for (int tile0 = tbeg; tile0 < tend; tile0 += T) {
+    const int tc = min(T, tend - tile0);
+    const float* p[T];
+    bool v[T];
+    float hi[T][MT][4], lo[T][MT][4];
+    float4 x[T];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+    for (int q = 0; q < T; ++q) {
+      const int r = 8 * (tile0 + q) + g;
+      v[q] = q < tc && r < n;
+      p[q] = Ag + static_cast<size_t>(v[q] ? r : 0) * lda + 4 * t;
+      x[q] = (v[q] && 0 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p[q])) : zero4;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) hi[nt][q] = lo[nt][q] = 0.f;
-    const int cmax = lda - 4 * t;  // column block kb is in range iff 16 * kb < cmax
-    float4 e0 = (v0 && 0 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0)) : zero4;
-    float4 f0 = (v1 && 0 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1)) : zero4;
-    float4 e1 = (v0 && 16 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0 + 16)) : zero4;
-    float4 f1 = (v1 && 16 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1 + 16)) : zero4;
-    for (int kb = 0; kb < KB; kb += 2) {
-      const float4 ce0 = e0, cf0 = f0, ce1 = e1, cf1 = f1;
-      const int c2 = 16 * (kb + 2), c3 = c2 + 16;
-      e0 = (v0 && c2 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0 + c2)) : zero4;
-      f0 = (v1 && c2 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1 + c2)) : zero4;
-      e1 = (v0 && c3 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p0 + c3)) : zero4;
-      f1 = (v1 && c3 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p1 + c3)) : zero4;
-      {
-        uint32_t eh[4], el[4], fh[4], fl[4];
-        split4(ce0, eh, el);
-        split4(cf0, fh, fl);
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float4 u = *reinterpret_cast<const float4*>(up + 8 * nt * ldt + 16 * kb);
-          uint32_t uh[4], ul[4];
-          split4(u, uh, ul);
-          mma_block<FULL>(hi[nt], lo[nt], eh, el, fh, fl, uh, ul);
-        }
+        for (int e = 0; e < 4; ++e) hi[q][mt][e] = lo[q][mt][e] = 0.f;
+    }
+    for (int kb = 0; kb < KB; ++kb) {
+      float4 cur[T];
+      const int nc = 16 * (kb + 1);
+#pragma unroll
+      for (int q = 0; q < T; ++q) {
+        cur[q] = x[q];
+        x[q] = (v[q] && nc < cmax) ? __ldcg(reinterpret_cast<const float4*>(p[q] + nc)) : zero4;
       }
-      if (kb + 1 < KB) {
-        uint32_t eh[4], el[4], fh[4], fl[4];
-        split4(ce1, eh, el);
-        split4(cf1, fh, fl);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float4 u = *reinterpret_cast<const float4*>(up + 8 * nt * ldt + 16 * (kb + 1));
-          uint32_t uh[4], ul[4];
-          split4(u, uh, ul);
-          mma_block<FULL>(hi[nt], lo[nt], eh, el, fh, fl, uh, ul);
+      for (int mt = 0; mt < MT; ++mt) {
+        const float* uf = Uf + ((kb * MT + mt) * 2) * 128 + lane * 4;
+        const float4 ua = *reinterpret_cast<const float4*>(uf);
+        const float4 ub = *reinterpret_cast<const float4*>(uf + 128);
+        uint32_t uah[4], ual[4], ubh[4], ubl[4];
+        split4(ua, uah, ual);
+        split4(ub, ubh, ubl);
+#pragma unroll
+        for (int q = 0; q < T; ++q) {
+          if (q < tc) {  // warp-uniform
+            const float4 c = cur[q];
+            if constexpr (FULL) {
+              mma_tf32(lo[q][mt], ual, __float_as_uint(c.x), __float_as_uint(c.y));
+              mma_tf32(lo[q][mt], uah, lo_bits(c.x), lo_bits(c.y));
+              mma_tf32(lo[q][mt], ubl, __float_as_uint(c.z), __float_as_uint(c.w));
+              mma_tf32(lo[q][mt], ubh, lo_bits(c.z), lo_bits(c.w));
+            }
+            mma_tf32(hi[q][mt], uah, __float_as_uint(c.x), __float_as_uint(c.y));
+            mma_tf32(hi[q][mt], ubh, __float_as_uint(c.z), __float_as_uint(c.w));
+          }
         }
       }
     }
-    const float d0 = v0 ? dinv[r0] : 0.f, d1 = v1 ? dinv[r1] : 0.f;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      float* y = Yt + (8 * nt + 2 * t) * ldt;
-      y[r0] = (hi[nt][0] + lo[nt][0]) * d0;
-      y[ldt + r0] = (hi[nt][1] + lo[nt][1]) * d0;
-      y[r1] = (hi[nt][2] + lo[nt][2]) * d1;
-      y[ldt + r1] = (hi[nt][3] + lo[nt][3]) * d1;
+    for (int q = 0; q < T; ++q) {
+      if (q < tc) {
+        const int i = 8 * (tile0 + q) + 2 * t;
+        const float2 dv = *reinterpret_cast<const float2*>(dinv + i);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int r0 = 16 * mt + g, r1 = r0 + 8;
+          if (r0 < rows)
+            *reinterpret_cast<float2*>(Yt + r0 * ldt + i) =
+                make_float2((hi[q][mt][0] + lo[q][mt][0]) * dv.x, (hi[q][mt][1] + lo[q][mt][1]) * dv.y);
+          if (r1 < rows)
+            *reinterpret_cast<float2*>(Yt + r1 * ldt + i) =
+                make_float2((hi[q][mt][2] + lo[q][mt][2]) * dv.x, (hi[q][mt][3] + lo[q][mt][3]) * dv.y);
+        }
+      }
     }
   }
 }
 
 // G[a][c] = sum_i dg[i] Q^T[a][i] Q^T[c][i]   and   H[a][c] = sum_i dg[i] P^T[a][i] Q^T[c][i]   (m x m, row
 // stride m + 1).  One warp per 16 x 8 output tile, the whole token range per warp: no cross-warp reduction.
+// Operands are 128-bit loads of 4 consecutive tokens per lane (same k permutation on both sides).
+template <int NWARPS>
 __device__ __forceinline__ void weighted_grams(const float* __restrict__ Pt, const float* __restrict__ Qt,
-                                               const float* __restrict__ dg, int n, int m, int ldt,
-                                               float* __restrict__ Gs, float* __restrict__ Hs, bool want_h,
-                                               int nwarps) {
+                                               const float* __restrict__ dg, int n, int m, int ldt, int rows,
+                                               float* __restrict__ Gs, float* __restrict__ Hs, bool want_h) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = (n + 15) >> 4;
-  const int MT = (m + 15) >> 4, NTg = (m + 7) >> 3;
-  const int per = MT * NTg;
+  const int MTg = (m + 15) >> 4, NTg = (m + 7) >> 3;
+  const int per = MTg * NTg;
   const int ntiles = want_h ? 2 * per : per;
   const int ld = m + 1;
-  for (int tile = warp; tile < ntiles; tile += nwarps) {
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tile = warp; tile < ntiles; tile += NWARPS) {
     const int mat = tile / per, rem = tile - mat * per;
     const int mt = rem / NTg, nt = rem - mt * NTg;
+    const bool v1 = 16 * mt + g + 8 < rows;
     const float* at = (mat == 0 ? Qt : Pt) + (16 * mt + g) * ldt + 4 * t;
     const float* bt = Qt + (8 * nt + g) * ldt + 4 * t;
     const float* dp = dg + 4 * t;
@@ -220,15 +233,20 @@ __device__ __forceinline__ void weighted_grams(const float* __restrict__ Pt, con
 #pragma unroll 2
     for (int kb = 0; kb < KB; ++kb) {
       const float4 a0 = *reinterpret_cast<const float4*>(at + 16 * kb);
-      const float4 a1 = *reinterpret_cast<const float4*>(at + 8 * ldt + 16 * kb);
+      const float4 a1 = v1 ? *reinterpret_cast<const float4*>(at + 8 * ldt + 16 * kb) : zero4;
       float4 b = *reinterpret_cast<const float4*>(bt + 16 * kb);
       const float4 d = *reinterpret_cast<const float4*>(dp + 16 * kb);
       b.x *= d.x; b.y *= d.y; b.z *= d.z; b.w *= d.w;
-      uint32_t eh[4], el[4], fh[4], fl[4], bh[4], bl[4];
-      split4(a0, eh, el);
-      split4(a1, fh, fl);
-      split4(b, bh, bl);
-      mma_block<true>(hi, lo, eh, el, fh, fl, bh, bl);
+      const uint32_t ah0[4] = {hi_bits(a0.x), hi_bits(a1.x), hi_bits(a0.y), hi_bits(a1.y)};
+      const uint32_t al0[4] = {lo_bits(a0.x), lo_bits(a1.x), lo_bits(a0.y), lo_bits(a1.y)};
+      const uint32_t ah1[4] = {hi_bits(a0.z), hi_bits(a1.z), hi_bits(a0.w), hi_bits(a1.w)};
+      const uint32_t al1[4] = {lo_bits(a0.z), lo_bits(a1.z), lo_bits(a0.w), lo_bits(a1.w)};
+      mma_tf32(lo, al0, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32(lo, ah0, lo_bits(b.x), lo_bits(b.y));
+      mma_tf32(lo, al1, __float_as_uint(b.z), __float_as_uint(b.w));
+      mma_tf32(lo, ah1, lo_bits(b.z), lo_bits(b.w));
+      mma_tf32(hi, ah0, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32(hi, ah1, __float_as_uint(b.z), __float_as_uint(b.w));
     }
     float* out = mat == 0 ? Gs : Hs;
     const int r0 = 16 * mt + g, r1 = r0 + 8, c0 = 8 * nt + 2 * t, c1 = c0 + 1;
@@ -240,93 +258,277 @@ __device__ __forceinline__ void weighted_grams(const float* __restrict__ Pt, con
   __syncthreads();
 }
 
+// Left operand W (m x m in shared memory, row stride ld) of the small products below, split once per warp.
+template <int MT>
+struct WFrag {
+  uint32_t hi[MT][2 * MT][4];
+  uint32_t lo[MT][2 * MT][4];
+};
+
+// w = W (or W^T) restricted to rows < mr and columns < mc
+template <int MT>
+__device__ __forceinline__ void load_wfrag(WFrag<MT>& w, const float* __restrict__ W, int ld, int mr, int mc,
+                                           bool transpose) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int ks = 0; ks < 2 * MT; ++ks) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = 16 * mt + g + 8 * (e & 1), c = 8 * ks + t + 4 * (e >> 1);
+        float x = 0.f;
+        if (r < mr && c < mc) x = transpose ? W[c * ld + r] : W[r * ld + c];
+        w.hi[mt][ks][e] = hi_bits(x);
+        w.lo[mt][ks][e] = lo_bits(x);
+      }
+    }
+  }
+}
+
+// acc[mt] = fragment of (W X^T)[16mt .. 16mt+15][i0 .. i0+7]
+template <int MT>
+__device__ __forceinline__ void tile_product(const WFrag<MT>& w, const float* __restrict__ Xt, int ldt, int rows,
+                                             int i0, float (&acc)[MT][4]) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float lo[MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[mt][e] = lo[mt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2 * MT; ++ks) {
+    const int ra = 8 * ks + t, rb = ra + 4;
+    const float x0 = ra < rows ? Xt[ra * ldt + i0 + g] : 0.f;
+    const float x1 = rb < rows ? Xt[rb * ldt + i0 + g] : 0.f;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      mma_tf32(lo[mt], w.lo[mt][ks], __float_as_uint(x0), __float_as_uint(x1));
+      mma_tf32(lo[mt], w.hi[mt][ks], lo_bits(x0), lo_bits(x1));
+      mma_tf32(acc[mt], w.hi[mt][ks], __float_as_uint(x0), __float_as_uint(x1));
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[mt][e] += lo[mt][e];
+}
+
+// Per-row sums held as fragment partials rs[mt][h] (row 16mt + 8h + g, summed over this lane's tokens):
+// out[r] = total over the CTA for r < nrows.  Shuffle over the 4 lanes of a row, then a fixed-order sum over warps.
+template <int MT, int NWARPS>
+__device__ __forceinline__ void reduce_rows(const float (&rs)[MT][2], int nrows, float* __restrict__ colred,
+                                            float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v = rs[mt][h];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t == 0) colred[warp * MSVIT_MAX_EIG_BLOCK + 16 * mt + 8 * h + g] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < nrows) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) v += colred[w * MSVIT_MAX_EIG_BLOCK + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// U^T <- W X^T  (W = L^-1: Cholesky QR) for all tokens, written both as the plain transposed block and in MMA
+// fragment order.  X^T may alias U^T: a warp reads its 8-token tile completely before it writes it.
+template <int MT, int NWARPS>
+__device__ __forceinline__ void orthonormalise(const float* __restrict__ W, int m, const float* Xt, float* Ut,
+                                               float* __restrict__ Uf, int npad, int ldt, int rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  WFrag<MT> w;
+  load_wfrag<MT>(w, W, m + 1, m, m, false);
+  for (int tile = warp; tile < (npad >> 3); tile += NWARPS) {
+    const int i0 = 8 * tile;
+    float acc[MT][4];
+    tile_product<MT>(w, Xt, ldt, rows, i0, acc);
+    const int j = i0 + 2 * t;
+    const int kb = j >> 4, tt = (j >> 2) & 3, ks = (j >> 1) & 1;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      if (r0 < rows) *reinterpret_cast<float2*>(Ut + r0 * ldt + j) = make_float2(acc[mt][0], acc[mt][1]);
+      if (r1 < rows) *reinterpret_cast<float2*>(Ut + r1 * ldt + j) = make_float2(acc[mt][2], acc[mt][3]);
+      *reinterpret_cast<float4*>(Uf + ((kb * MT + mt) * 2 + ks) * 128 + (g * 4 + tt) * 4) =
+          make_float4(acc[mt][0], acc[mt][2], acc[mt][1], acc[mt][3]);
+    }
+  }
+  __syncthreads();
+}
+
+// [U^T; Y^T] <- W [U^T; Y^T]  (Rayleigh-Ritz rotation) and res[c] = |y_c - theta_c u_c|_D^2 for c < kk.
+template <int MT, int NWARPS>
+__device__ __forceinline__ void rotate(const float* __restrict__ W, int m, float* Ut, float* Yt,
+                                       const float* __restrict__ dg, const float* __restrict__ theta, int kk,
+                                       int npad, int ldt, int rows, float* __restrict__ colred,
+                                       float* __restrict__ res) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  WFrag<MT> w;
+  load_wfrag<MT>(w, W, m + 1, m, m, false);
+  float rs[MT][2], th[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      rs[mt][h] = 0.f;
+      const int r = 16 * mt + 8 * h + g;
+      th[mt][h] = r < m ? theta[r] : 0.f;
+    }
+  for (int tile = warp; tile < (npad >> 3); tile += NWARPS) {
+    const int i0 = 8 * tile;
+    float au[MT][4], ay[MT][4];
+    tile_product<MT>(w, Ut, ldt, rows, i0, au);
+    tile_product<MT>(w, Yt, ldt, rows, i0, ay);
+    const int j = i0 + 2 * t;
+    const float2 d = *reinterpret_cast<const float2*>(dg + j);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      if (r0 < rows) {
+        *reinterpret_cast<float2*>(Ut + r0 * ldt + j) = make_float2(au[mt][0], au[mt][1]);
+        *reinterpret_cast<float2*>(Yt + r0 * ldt + j) = make_float2(ay[mt][0], ay[mt][1]);
+      }
+      if (r1 < rows) {
+        *reinterpret_cast<float2*>(Ut + r1 * ldt + j) = make_float2(au[mt][2], au[mt][3]);
+        *reinterpret_cast<float2*>(Yt + r1 * ldt + j) = make_float2(ay[mt][2], ay[mt][3]);
+      }
+      const float e0 = ay[mt][0] - th[mt][0] * au[mt][0], e1 = ay[mt][1] - th[mt][0] * au[mt][1];
+      const float e2 = ay[mt][2] - th[mt][1] * au[mt][2], e3 = ay[mt][3] - th[mt][1] * au[mt][3];
+      rs[mt][0] = fmaf(d.x * e0, e0, fmaf(d.y * e1, e1, rs[mt][0]));
+      rs[mt][1] = fmaf(d.x * e2, e2, fmaf(d.y * e3, e3, rs[mt][1]));
+    }
+  }
+  reduce_rows<MT, NWARPS>(rs, kk, colred, res);
+}
+
+// res[c] = |y_c - U h_c|_D^2 for c < kk  (h_c = column c of H): how far the leading columns are from span(U).
+template <int MT, int NWARPS>
+__device__ __forceinline__ void span_residuals(const float* __restrict__ Hs, int m, const float* __restrict__ Ut,
+                                               const float* __restrict__ Yt, const float* __restrict__ dg, int kk,
+                                               int npad, int ldt, int rows, float* __restrict__ colred,
+                                               float* __restrict__ res) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  WFrag<MT> w;
+  load_wfrag<MT>(w, Hs, m + 1, kk, m, true);  // rows c < kk of H^T
+  float rs[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) rs[mt][0] = rs[mt][1] = 0.f;
+  for (int tile = warp; tile < (npad >> 3); tile += NWARPS) {
+    const int i0 = 8 * tile;
+    float acc[MT][4];
+    tile_product<MT>(w, Ut, ldt, rows, i0, acc);
+    const int j = i0 + 2 * t;
+    const float2 d = *reinterpret_cast<const float2*>(dg + j);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      if (r0 < kk) {
+        const float2 y = *reinterpret_cast<const float2*>(Yt + r0 * ldt + j);
+        const float e0 = y.x - acc[mt][0], e1 = y.y - acc[mt][1];
+        rs[mt][0] = fmaf(d.x * e0, e0, fmaf(d.y * e1, e1, rs[mt][0]));
+      }
+      if (r1 < kk) {
+        const float2 y = *reinterpret_cast<const float2*>(Yt + r1 * ldt + j);
+        const float e2 = y.x - acc[mt][2], e3 = y.y - acc[mt][3];
+        rs[mt][1] = fmaf(d.x * e2, e2, fmaf(d.y * e3, e3, rs[mt][1]));
+      }
+    }
+  }
+  reduce_rows<MT, NWARPS>(rs, kk, colred, res);
+}
+
 // ----------------------------------------------------------------------------- small dense pieces
-// In-place Cholesky of the leading me x me block of G (row stride m + 1) by warp 0: lane i keeps row i in
-// registers, row j is broadcast by shuffles (left-looking), L is written back to the lower triangle and the
-// reciprocal pivots to pinv (0 for a dropped column).  Returns (to every thread) the smallest pivot of the
-// unit-diagonal-scaled matrix, i.e. a conditioning estimate that ignores column scaling.
+// Cholesky G = L L^T of the leading me x me block (row stride m + 1) and W = L^-1, both by warp 0.
+//   factorisation: lane i keeps row i in registers, row j is broadcast by shuffles (left-looking); L goes back to
+//                  the lower triangle of G, the reciprocal pivots to pinv (0 for a dropped, rank-deficient column);
+//   inverse:       lane j owns column j of W (forward substitution, L read back as warp-uniform loads).
+// Returns (to every thread) the smallest pivot of the unit-diagonal-scaled matrix, i.e. a conditioning
+// estimate that ignores column scaling.
 template <int MB>
-__device__ __forceinline__ float cholesky(float* __restrict__ G, int m, int me, float* __restrict__ pinv,
-                                          float* __restrict__ misc) {
+__device__ __forceinline__ float cholesky_inverse(float* __restrict__ G, int m, int me, float* __restrict__ pinv,
+                                                  float* __restrict__ W, float* __restrict__ misc) {
   const int ld = m + 1;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    const int row = lane < me ? lane : 0;
-    float g[MB];
+    {
+      const int row = lane < me ? lane : 0;
+      float g[MB];
 #pragma unroll
-    for (int c = 0; c < MB; ++c) g[c] = (c < me) ? G[row * ld + c] : 0.f;
-    float minpiv = 1.0f;
+      for (int c = 0; c < MB; ++c) g[c] = (c < me) ? G[row * ld + c] : 0.f;
+      float minpiv = 1.0f;
 #pragma unroll
-    for (int j = 0; j < MB; ++j) {
-      if (j < me) {  // warp-uniform
-        // s_i = G[i][j] - sum_{c<j} L[i][c] L[j][c]; lane j's value is the pivot
-        float s0 = g[j], s1 = 0.f;
+      for (int j = 0; j < MB; ++j) {
+        if (j < me) {  // warp-uniform
+          // s_i = G[i][j] - sum_{c<j} L[i][c] L[j][c]; lane j's value is the pivot
+          float s0 = g[j], s1 = 0.f;
 #pragma unroll
-        for (int c = 0; c + 1 < j; c += 2) {
-          s0 = fmaf(-g[c], __shfl_sync(0xffffffffu, g[c], j), s0);
-          s1 = fmaf(-g[c + 1], __shfl_sync(0xffffffffu, g[c + 1], j), s1);
+          for (int c = 0; c + 1 < j; c += 2) {
+            s0 = fmaf(-g[c], __shfl_sync(0xffffffffu, g[c], j), s0);
+            s1 = fmaf(-g[c + 1], __shfl_sync(0xffffffffu, g[c + 1], j), s1);
+          }
+          if (j & 1) s0 = fmaf(-g[j - 1], __shfl_sync(0xffffffffu, g[j - 1], j), s0);
+          const float s = s0 + s1;
+          const float piv = __shfl_sync(0xffffffffu, s, j);
+          const float gjj = __shfl_sync(0xffffffffu, g[j], j);
+          const float rel = gjj > 0.f ? piv / gjj : 0.f;
+          const bool ok = rel > 1e-6f && piv > 0.f;
+          minpiv = fminf(minpiv, ok ? rel : 1.0f);
+          const float ljj = ok ? sqrtf(piv) : 0.f;
+          const float inv = ok ? 1.0f / ljj : 0.f;
+          g[j] = lane == j ? ljj : (lane > j ? s * inv : 0.f);
+          if (lane == j) pinv[j] = inv;
         }
-        if (j & 1) s0 = fmaf(-g[j - 1], __shfl_sync(0xffffffffu, g[j - 1], j), s0);
-        const float s = s0 + s1;
-        const float piv = __shfl_sync(0xffffffffu, s, j);
-        const float gjj = __shfl_sync(0xffffffffu, g[j], j);
-        const float rel = gjj > 0.f ? piv / gjj : 0.f;
-        const bool ok = rel > 1e-6f && piv > 0.f;
-        minpiv = fminf(minpiv, ok ? rel : 1.0f);
-        const float ljj = ok ? sqrtf(piv) : 0.f;
-        const float inv = ok ? 1.0f / ljj : 0.f;
-        g[j] = lane == j ? ljj : (lane > j ? s * inv : 0.f);
-        if (lane == j) pinv[j] = inv;
+      }
+      if (lane < me) {
+#pragma unroll
+        for (int c = 0; c < MB; ++c)
+          if (c <= lane && c < me) G[lane * ld + c] = g[c];
+      }
+      if (lane == 0) misc[0] = minpiv;
+    }
+    __syncwarp();
+    {
+      // w_ij = pinv_i * (delta_ij - sum_{c<i} L[i][c] w_cj)
+      float w[MB];
+#pragma unroll
+      for (int i = 0; i < MB; ++i) {
+        float v = 0.f;
+        if (i < me) {  // warp-uniform
+          float s0 = (i == lane) ? 1.f : 0.f, s1 = 0.f;
+#pragma unroll
+          for (int c = 0; c + 1 < i; c += 2) {
+            s0 = fmaf(-G[i * ld + c], w[c], s0);
+            s1 = fmaf(-G[i * ld + c + 1], w[c + 1], s1);
+          }
+          if (i & 1) s0 = fmaf(-G[i * ld + i - 1], w[i - 1], s0);
+          v = (s0 + s1) * pinv[i];
+        }
+        w[i] = v;
+      }
+      if (lane < m) {
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+          if (i < m) W[i * ld + lane] = (i < me && lane <= i) ? w[i] : 0.f;
       }
     }
-    if (lane < me) {
-#pragma unroll
-      for (int c = 0; c < MB; ++c)
-        if (c <= lane && c < me) G[lane * ld + c] = g[c];
-    }
-    if (lane == 0) misc[0] = minpiv;
   }
   __syncthreads();
   return misc[0];
-}
-
-// X^T <- (Y L^-T)^T token by token (forward substitution), L from `cholesky`.  Columns with a zero pivot and
-// the pad tokens n .. npad-1 become 0.
-template <int MB>
-__device__ __forceinline__ void trisolve(float* __restrict__ Xt, const float* __restrict__ Yt, int n, int npad,
-                                         int me, int ldt, const float* __restrict__ L, int ld,
-                                         const float* __restrict__ pinv) {
-  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-    float y[MB];
-#pragma unroll
-    for (int c = 0; c < MB; ++c) y[c] = (c < me && i < n) ? Yt[c * ldt + i] : 0.f;
-#pragma unroll
-    for (int c = 0; c < MB; ++c) {
-      if (c < me) {
-        float s0 = y[c], s1 = 0.f;
-#pragma unroll
-        for (int a = 0; a + 1 < c; a += 2) {
-          s0 = fmaf(-y[a], L[c * ld + a], s0);
-          s1 = fmaf(-y[a + 1], L[c * ld + a + 1], s1);
-        }
-        if (c & 1) s0 = fmaf(-y[c - 1], L[c * ld + c - 1], s0);
-        y[c] = (s0 + s1) * pinv[c];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < MB; ++c)
-      if (c < me) Xt[c * ldt + i] = y[c];
-  }
-  __syncthreads();
-}
-
-// Round-robin tournament: partner of player i in round r (m even players, m - 1 rounds).
-__device__ __forceinline__ int rr_partner(int i, int r, int m) {
-  if (i == m - 1) return r;
-  int j = 2 * r - i;
-  if (j < 0) j += m - 1;
-  if (j >= m - 1) j -= m - 1;
-  return j == i ? m - 1 : j;
 }
 
 // Jacobi rotation that annihilates the (p, q) entry: J = [[c, s], [-s, c]] on (p, q), H' = J^T H J.
@@ -346,111 +548,104 @@ __device__ __forceinline__ void jacobi_rot(float app, float aqq, float apq, floa
   big = big || aabs > fmaxf(1e-4f * scale, 3e-8f);
 }
 
-// Symmetric eigen-decomposition of H (m x m, row stride m + 1, m even) by the whole CTA: parallel-order
-// two-sided Jacobi with one matrix entry per thread and one barrier per round (ping-pong buffers).
-// On exit H's diagonal holds the eigenvalues and Sm (same stride) the eigenvectors (columns).
+// Symmetric eigen-decomposition of the leading md x md block of H (row stride ld, md even) by the whole CTA:
+// parallel-order two-sided Jacobi.  Every round the md/2 rotations of a round-robin pairing are computed once
+// (one thread each), then every 2 x 2 block of J^T H J and every row pair of S J is updated in place by its
+// own thread.  On exit H's diagonal holds the eigenvalues and Sm (same stride) the eigenvectors (columns).
 // A sweep whose rotations were all below 1e-4 (relative) ends the iteration: convergence is quadratic.
-__device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int m, float* __restrict__ jac,
-                                       const uint8_t* __restrict__ ptab) {
-  const int ld = m + 1, mm = m * m;
+__device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int ld, int md, int max_sweeps,
+                                       float* __restrict__ rot) {
   const int nthreads = blockDim.x;
-  float* JH = jac;           // [2][mm]
-  float* JS = jac + 2 * mm;  // [2][mm]
-  for (int e = threadIdx.x; e < mm; e += nthreads) {
-    const int a = e / m, b = e - a * m;
-    JH[e] = 0.5f * (H[a * ld + b] + H[b * ld + a]);
-    JS[e] = a == b ? 1.f : 0.f;
+  for (int e = threadIdx.x; e < md * md; e += nthreads) {
+    const int a = e / md, b = e - a * md;
+    Sm[a * ld + b] = a == b ? 1.f : 0.f;
+    if (a < b) {
+      const float v = 0.5f * (H[a * ld + b] + H[b * ld + a]);
+      H[a * ld + b] = v;
+      H[b * ld + a] = v;
+    }
   }
   __syncthreads();
-  int cur = 0;
-  for (int sweep = 0; sweep < 10; ++sweep) {
+  const int half = md >> 1;
+  const int nb = half * half, ns = md * half;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     bool big = false;
-    for (int r = 0; r < m - 1; ++r) {
-      const float* __restrict__ hin = JH + cur * mm;
-      const float* __restrict__ sin_ = JS + cur * mm;
-      float* __restrict__ hout = JH + (cur ^ 1) * mm;
-      float* __restrict__ sout = JS + (cur ^ 1) * mm;
-      for (int e = threadIdx.x; e < mm; e += nthreads) {
-        const int a = e / m, b = e - a * m;
-        const int pa = ptab[r * m + a], pb = ptab[r * m + b];
-        const int p1 = min(a, pa), q1 = max(a, pa), p2 = min(b, pb), q2 = max(b, pb);
-        float c1, s1, c2, s2;
-        bool dummy = false;
-        jacobi_rot(hin[p1 * m + p1], hin[q1 * m + q1], hin[p1 * m + q1], c1, s1, dummy);
-        jacobi_rot(hin[p2 * m + p2], hin[q2 * m + q2], hin[p2 * m + q2], c2, s2, big);
-        const float g1 = a < pa ? -s1 : s1;  // coefficient of the partner row
-        const float g2 = b < pb ? -s2 : s2;  // coefficient of the partner column
-        const float v = c1 * fmaf(g2, hin[a * m + pb], c2 * hin[e]) + g1 * fmaf(g2, hin[pa * m + pb], c2 * hin[pa * m + b]);
-        hout[e] = pa == b ? 0.f : v;
-        sout[e] = fmaf(g2, sin_[a * m + pb], c2 * sin_[e]);
+    for (int r = 0; r < md - 1; ++r) {
+      if (threadIdx.x < half) {
+        const int tq = threadIdx.x;
+        int p, q;
+        if (tq == 0) { p = r; q = md - 1; }
+        else {
+          p = r + tq; if (p >= md - 1) p -= md - 1;
+          q = r - tq; if (q < 0) q += md - 1;
+        }
+        if (p > q) { const int x = p; p = q; q = x; }
+        float c, s;
+        jacobi_rot(H[p * ld + p], H[q * ld + q], H[p * ld + q], c, s, big);
+        *reinterpret_cast<float4*>(rot + 4 * tq) = make_float4(c, s, __int_as_float(p), __int_as_float(q));
       }
-      cur ^= 1;
+      __syncthreads();
+      for (int item = threadIdx.x; item < nb + ns; item += nthreads) {
+        if (item < nb) {
+          // H[P1][P2] <- J1^T H[P1][P2] J2
+          const int t1 = item / half, t2 = item - t1 * half;
+          const float4 r1 = *reinterpret_cast<const float4*>(rot + 4 * t1);
+          const float4 r2 = *reinterpret_cast<const float4*>(rot + 4 * t2);
+          const int p1 = __float_as_int(r1.z), q1 = __float_as_int(r1.w);
+          const int p2 = __float_as_int(r2.z), q2 = __float_as_int(r2.w);
+          const float hpp = H[p1 * ld + p2], hpq = H[p1 * ld + q2], hqp = H[q1 * ld + p2], hqq = H[q1 * ld + q2];
+          const float rpp = r1.x * hpp - r1.y * hqp, rpq = r1.x * hpq - r1.y * hqq;
+          const float rqp = r1.y * hpp + r1.x * hqp, rqq = r1.y * hpq + r1.x * hqq;
+          float npp = r2.x * rpp - r2.y * rpq, npq = r2.y * rpp + r2.x * rpq;
+          float nqp = r2.x * rqp - r2.y * rqq, nqq = r2.y * rqp + r2.x * rqq;
+          if (t1 == t2) { npq = 0.f; nqp = 0.f; }
+          H[p1 * ld + p2] = npp; H[p1 * ld + q2] = npq; H[q1 * ld + p2] = nqp; H[q1 * ld + q2] = nqq;
+        } else {
+          // S[:, P2] <- S[:, P2] J2
+          const int e = item - nb;
+          const int a = e / half, t2 = e - a * half;
+          const float4 r2 = *reinterpret_cast<const float4*>(rot + 4 * t2);
+          const int p2 = __float_as_int(r2.z), q2 = __float_as_int(r2.w);
+          const float sp = Sm[a * ld + p2], sq = Sm[a * ld + q2];
+          Sm[a * ld + p2] = r2.x * sp - r2.y * sq;
+          Sm[a * ld + q2] = r2.y * sp + r2.x * sq;
+        }
+      }
       __syncthreads();
     }
     if (!__syncthreads_or(big ? 1 : 0)) break;
   }
-  const float* __restrict__ hf = JH + cur * mm;
-  const float* __restrict__ sf = JS + cur * mm;
-  for (int e = threadIdx.x; e < mm; e += nthreads) {
-    const int a = e / m, b = e - a * m;
-    H[a * ld + b] = hf[e];
-    Sm[a * ld + b] = sf[e];
-  }
-  __syncthreads();
 }
 
-// Per-column sums of per-thread partials: out[c] = sum over threads of rloc[c].  Warp shuffle reduction, then a
-// fixed-order sum over warps (deterministic).
-template <int MB>
-__device__ __forceinline__ void reduce_columns(const float (&rloc)[MB], int ncols, float* __restrict__ colred,
-                                               float* __restrict__ out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-#pragma unroll
-  for (int c = 0; c < MB; ++c) {
-    if (c < ncols) {
-      const float v = warp_sum(rloc[c]);
-      if (lane == 0) colred[warp * MSVIT_MAX_EIG_BLOCK + c] = v;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < ncols) {
-    float v = 0.f;
-    for (int w = 0; w < nwarps; ++w) v += colred[w * MSVIT_MAX_EIG_BLOCK + threadIdx.x];
-    out[threadIdx.x] = v;
-  }
-  __syncthreads();
-}
-
-// NT: 8-column tiles of the block (m <= 8 * NT).  THREADS: CTA size.
-template <int NT, int THREADS>
+// MT: 16-row tiles of the block (m <= 16 * MT).  THREADS: CTA size.
+template <int MT, int THREADS>
 __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS) : 1) ncut_eig_kernel(const Params P) {
-  constexpr int MB = 8 * NT;
-  constexpr int ROWS = NT > 2 ? 32 : 16;
+  constexpr int MB = 16 * MT;
   constexpr int NWARPS = THREADS / 32;
+  constexpr int T = MT == 1 ? 4 : 2;
   extern __shared__ __align__(16) float smem[];
-  const Layout L = make_layout(P.N, P.m, ROWS, NWARPS);
+  const Layout L = make_layout(P.N, P.m, MT, NWARPS);
   float* Ut = smem + L.Ut;
   float* Yt = smem + L.Yt;
+  float* Uf = smem + L.Uf;
   float* dg = smem + L.dg;
   float* dinv = smem + L.dinv;
   float* Gs = smem + L.Gs;
   float* Hs = smem + L.Hs;
   float* Ss = smem + L.Ss;
+  float* Ws = smem + L.Ws;
   float* pinv = smem + L.pinv;
   float* misc = smem + L.misc;           // [0] = scalar broadcast, [1] = worst residual, [2] = trigger flag
   float* theta = misc + 8;               // [m] Ritz values in sorted order
   float* res = theta + MSVIT_MAX_EIG_BLOCK;   // [m] squared residuals / column signs
   int* order = reinterpret_cast<int*>(res + MSVIT_MAX_EIG_BLOCK);  // [m] sorted position -> Jacobi column
   float* colred = smem + L.colred;
-  float* jac = smem + L.jac;
-  uint8_t* ptab = reinterpret_cast<uint8_t*>(smem + L.ptab);
-  const int ldt = L.ldt;
+  float* rot = smem + L.rot;
+  const int ldt = L.ldt, rows = L.rows;
 
   const int m = P.m, k = P.k;
   const int ld = m + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int e = threadIdx.x; e < (m - 1) * m; e += THREADS) ptab[e] = static_cast<uint8_t>(rr_partner(e % m, e / m, m));
 
   for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
     const Seg g = seg_info(s, P.N, P.seg_off, P.a_off);
@@ -468,14 +663,14 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
     const int kk = k < me ? k : me;  // wanted pairs that exist
     const int npad = ((n + 15) >> 4) << 4;
 
-    // ---- load: degree, start block (pad tokens and pad columns are zero)
+    // ---- load: degree, start block (pad tokens and pad rows are zero)
     __syncthreads();  // the previous segment's readers of the shared arrays are done
     for (int i = threadIdx.x; i < npad; i += THREADS) {
       const float d = i < n ? P.deg[g.row0 + i] : 0.f;
       dg[i] = d;
       dinv[i] = d > 0.f ? 1.0f / d : 0.f;
     }
-    for (int e = threadIdx.x; e < ROWS * npad; e += THREADS) {
+    for (int e = threadIdx.x; e < rows * npad; e += THREADS) {
       const int c = e / npad, i = e - c * npad;
       float v = 0.f;
       if (c < me && i < n) {
@@ -488,43 +683,25 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
     __syncthreads();
 
     // ---- D-orthonormalise the start block
-    weighted_grams(Ut, Ut, dg, n, m, ldt, Gs, Hs, false, NWARPS);
-    cholesky<MB>(Gs, m, me, pinv, misc);
-    trisolve<MB>(Ut, Ut, n, npad, me, ldt, Gs, ld, pinv);
+    weighted_grams<NWARPS>(Ut, Ut, dg, n, m, ldt, rows, Gs, Hs, false);
+    cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
+    orthonormalise<MT, NWARPS>(Ws, m, Ut, Ut, Uf, npad, ldt, rows);
 
     int it = 0;
     const float tol2 = P.tol * P.tol;
     while (true) {
       ++it;
-      if (it <= P.fast_iters) matvec<NT, false>(Ag, lda, n, Ut, Yt, dinv, ldt, NWARPS);
-      else matvec<NT, true>(Ag, lda, n, Ut, Yt, dinv, ldt, NWARPS);
+      if (it <= P.fast_iters) matvec<MT, T, false, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
+      else matvec<MT, T, true, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
       __syncthreads();
       const bool last = it >= P.max_iter || n <= m;  // n <= m: span(U) is the whole space, one step is exact
       // ---- G = Y^T D Y, H = U^T D Y (U is D-orthonormal) and the trigger: for each wanted column j
       //        |y_j - U h_j|_D^2 + sum_{a >= kk} H[a][j]^2   =   residual of the Ritz problem on the leading columns
-      weighted_grams(Ut, Yt, dg, n, m, ldt, Gs, Hs, true, NWARPS);
-      bool do_rr = last || (it % P.rr_every) == 0;
-      if (!do_rr && it >= 2 && it > P.fast_iters) {
-        float rloc[MB];
-#pragma unroll
-        for (int c = 0; c < MB; ++c) rloc[c] = 0.f;
-        for (int i = threadIdx.x; i < n; i += THREADS) {
-          float u[MB];
-#pragma unroll
-          for (int a = 0; a < MB; ++a) u[a] = a < m ? Ut[a * ldt + i] : 0.f;
-          const float d = dg[i];
-#pragma unroll
-          for (int c = 0; c < MB; ++c) {
-            if (c < kk) {
-              float r = Yt[c * ldt + i];
-#pragma unroll
-              for (int a = 0; a < MB; ++a)
-                if (a < m) r = fmaf(-u[a], Hs[a * ld + c], r);
-              rloc[c] = fmaf(d * r, r, rloc[c]);
-            }
-          }
-        }
-        reduce_columns<MB>(rloc, kk, colred, res);
+      weighted_grams<NWARPS>(Ut, Yt, dg, n, m, ldt, rows, Gs, Hs, true);
+      const bool scheduled = last || (it % P.rr_every) == 0;
+      bool fired = false;
+      if (!scheduled && it >= 2 && it > P.fast_iters) {
+        span_residuals<MT, NWARPS>(Hs, m, Ut, Yt, dg, kk, npad, ldt, rows, colred, res);
         if (threadIdx.x == 0) {
           float worst = 0.f;
           for (int c = 0; c < kk; ++c) {
@@ -535,57 +712,41 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
           misc[2] = worst <= tol2 ? 1.f : 0.f;
         }
         __syncthreads();
-        do_rr = misc[2] != 0.f;
+        fired = misc[2] != 0.f;
       }
       bool rotated = false;
-      if (do_rr) {
-        // ---- Rayleigh-Ritz on span(U)
-        jacobi(Hs, Ss, m, jac, ptab);
+      if (scheduled || fired) {
+        // ---- Rayleigh-Ritz: the whole block (scheduled; a few sweeps unless it is the last step), or only the
+        //      leading columns once they span an invariant subspace (trigger; to full accuracy)
+        int md = m, sweeps = last ? 12 : 3;
+        if (!scheduled) {
+          const int mdb = (kk + 1) & ~1;
+          if (mdb <= me) { md = mdb; sweeps = 12; }
+        }
+        jacobi(Hs, Ss, ld, md, sweeps, rot);
         if (threadIdx.x < m) {
           const int a = threadIdx.x;
           const float ta = Hs[a * ld + a];
-          int rank = 0;
-          for (int b = 0; b < m; ++b) {
-            const float tb = Hs[b * ld + b];
-            rank += (tb > ta || (tb == ta && b < a)) ? 1 : 0;
+          if (a < md) {
+            int rank = 0;
+            for (int b = 0; b < md; ++b) {
+              const float tb = Hs[b * ld + b];
+              rank += (tb > ta || (tb == ta && b < a)) ? 1 : 0;
+            }
+            order[rank] = a;
+            theta[rank] = ta;
+          } else {
+            order[a] = a;
+            theta[a] = ta;
           }
-          order[rank] = a;
-          theta[rank] = ta;
         }
         __syncthreads();
-        // rotate U and Y into the Ritz basis, accumulate weighted residuals of the wanted pairs
-        float rloc[MB];
-#pragma unroll
-        for (int c = 0; c < MB; ++c) rloc[c] = 0.f;
-        for (int i = threadIdx.x; i < n; i += THREADS) {
-          float u[MB], y[MB];
-#pragma unroll
-          for (int c = 0; c < MB; ++c) {
-            u[c] = c < m ? Ut[c * ldt + i] : 0.f;
-            y[c] = c < m ? Yt[c * ldt + i] : 0.f;
-          }
-          const float d = dg[i];
-#pragma unroll
-          for (int c = 0; c < MB; ++c) {
-            if (c < m) {
-              const int col = order[c];
-              float nu = 0.f, ny = 0.f;
-#pragma unroll
-              for (int a = 0; a < MB; ++a) {
-                if (a < m) {
-                  const float sv = Ss[a * ld + col];
-                  nu = fmaf(u[a], sv, nu);
-                  ny = fmaf(y[a], sv, ny);
-                }
-              }
-              Ut[c * ldt + i] = nu;
-              Yt[c * ldt + i] = ny;
-              const float rr = ny - theta[c] * nu;
-              rloc[c] = fmaf(d * rr, rr, rloc[c]);
-            }
-          }
+        for (int e = threadIdx.x; e < m * m; e += THREADS) {
+          const int c = e / m, a = e - c * m;
+          Ws[c * ld + a] = (c < md && a < md) ? Ss[a * ld + order[c]] : (a == c ? 1.f : 0.f);
         }
-        reduce_columns<MB>(rloc, kk, colred, res);
+        __syncthreads();
+        rotate<MT, NWARPS>(Ws, m, Ut, Yt, dg, theta, kk, npad, ldt, rows, colred, res);
         if (threadIdx.x == 0) {
           float worst = 0.f;
           for (int c = 0; c < kk; ++c)
@@ -597,13 +758,13 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
         rotated = true;
       }
       // ---- U = orth_D(Y)
-      if (rotated) weighted_grams(Ut, Yt, dg, n, m, ldt, Gs, Hs, false, NWARPS);  // G of the rotated Y
-      const float piv = cholesky<MB>(Gs, m, me, pinv, misc);
-      trisolve<MB>(Ut, Yt, n, npad, me, ldt, Gs, ld, pinv);
+      if (rotated) weighted_grams<NWARPS>(Ut, Yt, dg, n, m, ldt, rows, Gs, Hs, false);  // G of the rotated Y
+      const float piv = cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
+      orthonormalise<MT, NWARPS>(Ws, m, Yt, Ut, Uf, npad, ldt, rows);
       if (piv < 0.05f) {
-        weighted_grams(Ut, Ut, dg, n, m, ldt, Gs, Hs, false, NWARPS);
-        cholesky<MB>(Gs, m, me, pinv, misc);
-        trisolve<MB>(Ut, Ut, n, npad, me, ldt, Gs, ld, pinv);
+        weighted_grams<NWARPS>(Ut, Ut, dg, n, m, ldt, rows, Gs, Hs, false);
+        cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
+        orthonormalise<MT, NWARPS>(Ws, m, Ut, Ut, Uf, npad, ldt, rows);
       }
     }
 
@@ -640,31 +801,30 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
   }
 }
 
-template <int NT, int THREADS>
+template <int MT, int THREADS>
 static int launch(const Params& P, cudaStream_t stream) {
-  constexpr int ROWS = NT > 2 ? 32 : 16;
-  const size_t smem = static_cast<size_t>(make_layout(P.N, P.m, ROWS, THREADS / 32).total) * 4;
+  const size_t smem = static_cast<size_t>(make_layout(P.N, P.m, MT, THREADS / 32).total) * 4;
   const size_t kMaxSmem = 227 * 1024;
   if (smem > kMaxSmem) return MSVIT_ERR_SHAPE;
-  cudaError_t e = cudaFuncSetAttribute(ncut_eig_kernel<NT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(ncut_eig_kernel<MT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_status(e);
   int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncut_eig_kernel<NT, THREADS>, THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncut_eig_kernel<MT, THREADS>, THREADS, smem);
   if (e != cudaSuccess) return cuda_status(e);
   if (per_sm < 1) per_sm = 1;
   // one CTA per segment while that is at most a few waves, else a persistent grid-stride loop
   const long long cap = 16LL * per_sm * sm_count();
   const int grid = static_cast<int>(P.S < cap ? P.S : cap);
-  ncut_eig_kernel<NT, THREADS><<<grid, THREADS, smem, stream>>>(P);
+  ncut_eig_kernel<MT, THREADS><<<grid, THREADS, smem, stream>>>(P);
   return cuda_status(cudaGetLastError());
 }
 
-template <int NT>
+template <int MT>
 static int launch_threads(const Params& P, cudaStream_t stream) {
-  if (P.N <= 256) return launch<NT, 128>(P, stream);
-  if (P.N <= 512) return launch<NT, 256>(P, stream);
-  return launch<NT, 512>(P, stream);
+  if (P.N <= 256) return launch<MT, 128>(P, stream);
+  if (P.N <= 512) return launch<MT, 256>(P, stream);
+  return launch<MT, 512>(P, stream);
 }
 
 }  // namespace eig
@@ -689,7 +849,6 @@ extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float*
   P.S = S; P.N = N; P.k = k; P.m = block;
   P.max_iter = max_iter; P.rr_every = 3; P.tol = tol; P.lam_floor = lam_floor;
   P.fast_iters = 0;
-  if (block <= 16) return launch_threads<2>(P, stream);
-  if (block <= 24) return launch_threads<3>(P, stream);
-  return launch_threads<4>(P, stream);
+  if (block <= 16) return launch_threads<1>(P, stream);
+  return launch_threads<2>(P, stream);
 }
