@@ -35,8 +35,44 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
+// Tuning knobs (compile-time; the defaults are what ships, the others exist for tools/microbench/eig_variants.py)
+#ifndef EIG_T          // 8-row tiles of A per matvec pass when m <= 16
+#define EIG_T 4
+#endif
+#ifndef EIG_PF         // 16-column blocks of A in flight per lane in the matvec
+#define EIG_PF 4
+#endif
+#ifndef EIG_MINB       // CTAs per SM the register budget is sized for, at 128 threads
+#define EIG_MINB 4
+#endif
+#ifndef EIG_RR_EVERY   // scheduled whole-block Rayleigh-Ritz period
+#define EIG_RR_EVERY 3
+#endif
+#ifndef EIG_SWEEPS     // Jacobi sweeps of a scheduled (not final) Rayleigh-Ritz step
+#define EIG_SWEEPS 3
+#endif
+#ifndef EIG_FAST_ITERS // leading products done in a single TF32 pass
+#define EIG_FAST_ITERS 0
+#endif
+
 namespace msvit {
 namespace eig {
+
+#ifdef EIG_PROFILE
+// Development instrumentation: cycles thread 0 of every CTA spends in each phase (tools/microbench/eig_variants.py).
+enum { PH_INIT, PH_MATVEC, PH_GRAMS, PH_TRIGGER, PH_JACOBI, PH_ROTATE, PH_CHOL, PH_ORTH, PH_OUTPUT, PH_COUNT };
+__device__ unsigned long long g_phase_cycles[PH_COUNT];
+#define PHASE_BEGIN() long long ph_t0 = clock64()
+#define PHASE_END(ph)                                                                          \
+  do {                                                                                         \
+    const long long ph_t1 = clock64();                                                         \
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[ph], (unsigned long long)(ph_t1 - ph_t0)); \
+    ph_t0 = ph_t1;                                                                             \
+  } while (0)
+#else
+#define PHASE_BEGIN()
+#define PHASE_END(ph)
+#endif
 
 struct Params {
   const float* A;
@@ -123,9 +159,103 @@ __device__ __forceinline__ void split4(const float4& v, uint32_t (&hi)[4], uint3
 // The matching right operand of 8 rows of A is one 128-bit load per lane: x = A[i0+g][16kb+4t .. +3],
 // (b0, b1) = (x.x, x.y) for ks = 0 and (x.z, x.w) for ks = 1.
 
+// position of U^T[c][j] in the fragment-order copy
+template <int MT>
+__device__ __forceinline__ int uf_index(int c, int j) {
+  const int kb = j >> 4, tt = (j >> 2) & 3, ks = (j >> 1) & 1, kh = j & 1;
+  const int mt = c >> 4, half = (c >> 3) & 1, cg = c & 7;
+  return ((kb * MT + mt) * 2 + ks) * 128 + (cg * 4 + tt) * 4 + kh * 2 + half;
+}
+
+// One 16-column block of the product for TC row tiles: acc[q] += Ufrag(kb) * x[q]^T.
+template <int MT, int TC, bool FULL>
+__device__ __forceinline__ void matvec_block(float (&acc)[TC][MT][4], const float4 (&x)[TC],
+                                             const float* __restrict__ uf, int kb) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const float4 ua = *reinterpret_cast<const float4*>(uf + ((kb * MT + mt) * 2) * 128);
+    const float4 ub = *reinterpret_cast<const float4*>(uf + ((kb * MT + mt) * 2 + 1) * 128);
+    uint32_t uah[4], ual[4], ubh[4], ubl[4];
+    split4(ua, uah, ual);
+    split4(ub, ubh, ubl);
+#pragma unroll
+    for (int q = 0; q < TC; ++q) {
+      const float4 c = x[q];
+      if constexpr (FULL) {
+        mma_tf32(acc[q][mt], ual, __float_as_uint(c.x), __float_as_uint(c.y));
+        mma_tf32(acc[q][mt], uah, lo_bits(c.x), lo_bits(c.y));
+        mma_tf32(acc[q][mt], ubl, __float_as_uint(c.z), __float_as_uint(c.w));
+        mma_tf32(acc[q][mt], ubh, lo_bits(c.z), lo_bits(c.w));
+      }
+      mma_tf32(acc[q][mt], uah, __float_as_uint(c.x), __float_as_uint(c.y));
+      mma_tf32(acc[q][mt], ubh, __float_as_uint(c.z), __float_as_uint(c.w));
+    }
+  }
+}
+
+// TC consecutive 8-row tiles of A starting at tile0, all 16-column blocks: EIG_PF blocks in flight per lane (a
+// rolling register window, refilled right after a block's MMAs are issued), rows past the end are clamped
+// (their products are scaled by dinv = 0).
+template <int MT, int TC, bool FULL>
+__device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int lda, int n, int KB, bool last_ok,
+                                            const float* __restrict__ uf, float* __restrict__ Yt,
+                                            const float* __restrict__ dinv, int ldt, int rows, int tile0, int g,
+                                            int t) {
+  constexpr int PF = EIG_PF;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t off[TC];
+  float acc[TC][MT][4];
+  float4 x[PF][TC];
+#pragma unroll
+  for (int q = 0; q < TC; ++q) {
+    const int r = min(8 * (tile0 + q) + g, n - 1);
+    off[q] = static_cast<uint32_t>(r) * static_cast<uint32_t>(lda) + 4u * t;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[q][mt][e] = 0.f;
+  }
+#pragma unroll
+  for (int s = 0; s < PF; ++s) {
+    const bool ok = s + 1 < KB || (s < KB && last_ok);
+    const float* ak = Ag + 16 * s;
+#pragma unroll
+    for (int q = 0; q < TC; ++q) x[s][q] = ok ? __ldcg(reinterpret_cast<const float4*>(ak + off[q])) : zero4;
+  }
+  for (int kb0 = 0; kb0 < KB; kb0 += PF) {
+#pragma unroll
+    for (int s = 0; s < PF; ++s) {
+      const int kb = kb0 + s;
+      if (kb < KB) {  // warp-uniform
+        matvec_block<MT, TC, FULL>(acc, x[s], uf, kb);
+        const int nk = kb + PF;
+        if (nk < KB) {
+          const bool ok = nk + 1 < KB || last_ok;
+          const float* ak = Ag + 16 * nk;
+#pragma unroll
+          for (int q = 0; q < TC; ++q) x[s][q] = ok ? __ldcg(reinterpret_cast<const float4*>(ak + off[q])) : zero4;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < TC; ++q) {
+    const int i = 8 * (tile0 + q) + 2 * t;
+    const float2 dv = *reinterpret_cast<const float2*>(dinv + i);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      if (r0 < rows)
+        *reinterpret_cast<float2*>(Yt + r0 * ldt + i) = make_float2(acc[q][mt][0] * dv.x, acc[q][mt][1] * dv.y);
+      if (r1 < rows)
+        *reinterpret_cast<float2*>(Yt + r1 * ldt + i) = make_float2(acc[q][mt][2] * dv.x, acc[q][mt][3] * dv.y);
+    }
+  }
+}
+
 // Y^T[c][i] = dinv[i] * sum_j U^T[c][j] A[i][j]   (A symmetric).  Each warp owns a contiguous range of 8-row tiles of
-// A and works on T of them at a time so that one U fragment load feeds T MMAs; A comes straight from global
-// memory (L2), the next 16-column block is in flight while the current one is multiplied.
+// A and works on up to T of them at a time so that one U fragment load feeds T MMAs; A comes straight from global
+// memory (L2).
 template <int MT, int T, bool FULL, int NWARPS>
 __device__ __forceinline__ void matvec(const float* __restrict__ Ag, int lda, int n, const float* __restrict__ Uf,
                                        float* __restrict__ Yt, const float* __restrict__ dinv, int ldt, int rows) {
@@ -136,75 +266,20 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Ag, int lda, in
   const int per = (ntile + NWARPS - 1) / NWARPS;
   const int tbeg = warp * per;
   const int tend = min(ntile, tbeg + per);
-  const int cmax = lda - 4 * t;  // column block kb is in range iff 16 * kb < cmax
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int tile0 = tbeg; tile0 < tend; tile0 += T) {
-    const int tc = min(T, tend - tile0);
-    const float* p[T];
-    bool v[T];
-    float hi[T][MT][4], lo[T][MT][4];
-    float4 x[T];
-#pragma unroll
-    for (int q = 0; q < T; ++q) {
-      const int r = 8 * (tile0 + q) + g;
-      v[q] = q < tc && r < n;
-      p[q] = Ag + static_cast<size_t>(v[q] ? r : 0) * lda + 4 * t;
-      x[q] = (v[q] && 0 < cmax) ? __ldcg(reinterpret_cast<const float4*>(p[q])) : zero4;
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) hi[q][mt][e] = lo[q][mt][e] = 0.f;
-    }
-    for (int kb = 0; kb < KB; ++kb) {
-      float4 cur[T];
-      const int nc = 16 * (kb + 1);
-#pragma unroll
-      for (int q = 0; q < T; ++q) {
-        cur[q] = x[q];
-        x[q] = (v[q] && nc < cmax) ? __ldcg(reinterpret_cast<const float4*>(p[q] + nc)) : zero4;
-      }
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const float* uf = Uf + ((kb * MT + mt) * 2) * 128 + lane * 4;
-        const float4 ua = *reinterpret_cast<const float4*>(uf);
-        const float4 ub = *reinterpret_cast<const float4*>(uf + 128);
-        uint32_t uah[4], ual[4], ubh[4], ubl[4];
-        split4(ua, uah, ual);
-        split4(ub, ubh, ubl);
-#pragma unroll
-        for (int q = 0; q < T; ++q) {
-          if (q < tc) {  // warp-uniform
-            const float4 c = cur[q];
-            if constexpr (FULL) {
-              mma_tf32(lo[q][mt], ual, __float_as_uint(c.x), __float_as_uint(c.y));
-              mma_tf32(lo[q][mt], uah, lo_bits(c.x), lo_bits(c.y));
-              mma_tf32(lo[q][mt], ubl, __float_as_uint(c.z), __float_as_uint(c.w));
-              mma_tf32(lo[q][mt], ubh, lo_bits(c.z), lo_bits(c.w));
-            }
-            mma_tf32(hi[q][mt], uah, __float_as_uint(c.x), __float_as_uint(c.y));
-            mma_tf32(hi[q][mt], ubh, __float_as_uint(c.z), __float_as_uint(c.w));
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < T; ++q) {
-      if (q < tc) {
-        const int i = 8 * (tile0 + q) + 2 * t;
-        const float2 dv = *reinterpret_cast<const float2*>(dinv + i);
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int r0 = 16 * mt + g, r1 = r0 + 8;
-          if (r0 < rows)
-            *reinterpret_cast<float2*>(Yt + r0 * ldt + i) =
-                make_float2((hi[q][mt][0] + lo[q][mt][0]) * dv.x, (hi[q][mt][1] + lo[q][mt][1]) * dv.y);
-          if (r1 < rows)
-            *reinterpret_cast<float2*>(Yt + r1 * ldt + i) =
-                make_float2((hi[q][mt][2] + lo[q][mt][2]) * dv.x, (hi[q][mt][3] + lo[q][mt][3]) * dv.y);
-        }
-      }
-    }
+  // every 16-column block but the last lies inside the row; the last one is cut at lda (a multiple of 4)
+  const bool last_ok = 16 * (KB - 1) + 4 * t < lda;
+  const float* uf = Uf + lane * 4;
+  int tile0 = tbeg;
+  for (; tile0 + T <= tend; tile0 += T)
+    matvec_pass<MT, T, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
+  const int left = tend - tile0;
+  if constexpr (T > 3) {
+    if (left == 3) matvec_pass<MT, 3, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
   }
+  if constexpr (T > 2) {
+    if (left == 2) matvec_pass<MT, 2, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
+  }
+  if (left == 1) matvec_pass<MT, 1, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
 }
 
 // G[a][c] = sum_i dg[i] Q^T[a][i] Q^T[c][i]   and   H[a][c] = sum_i dg[i] P^T[a][i] Q^T[c][i]   (m x m, row
@@ -485,11 +560,15 @@ __device__ __forceinline__ float cholesky_inverse(float* __restrict__ G, int m, 
           const float s = s0 + s1;
           const float piv = __shfl_sync(0xffffffffu, s, j);
           const float gjj = __shfl_sync(0xffffffffu, g[j], j);
-          const float rel = gjj > 0.f ? piv / gjj : 0.f;
+          const float rel = gjj > 0.f ? __fdividef(piv, gjj) : 0.f;
           const bool ok = rel > 1e-6f && piv > 0.f;
           minpiv = fminf(minpiv, ok ? rel : 1.0f);
-          const float ljj = ok ? sqrtf(piv) : 0.f;
-          const float inv = ok ? 1.0f / ljj : 0.f;
+          float inv = 0.f, ljj = 0.f;
+          if (ok) {
+            inv = rsqrtf(piv);
+            inv = inv * (1.5f - 0.5f * piv * inv * inv);  // one Newton step: fp32-accurate 1/sqrt
+            ljj = piv * inv;
+          }
           g[j] = lane == j ? ljj : (lane > j ? s * inv : 0.f);
           if (lane == j) pinv[j] = inv;
         }
@@ -548,15 +627,22 @@ __device__ __forceinline__ void jacobi_rot(float app, float aqq, float apq, floa
   big = big || aabs > fmaxf(1e-4f * scale, 3e-8f);
 }
 
-// Symmetric eigen-decomposition of the leading md x md block of H (row stride ld, md even) by the whole CTA:
-// parallel-order two-sided Jacobi.  Every round the md/2 rotations of a round-robin pairing are computed once
-// (one thread each), then every 2 x 2 block of J^T H J and every row pair of S J is updated in place by its
-// own thread.  On exit H's diagonal holds the eigenvalues and Sm (same stride) the eigenvectors (columns).
-// A sweep whose rotations were all below 1e-4 (relative) ends the iteration: convergence is quadratic.
-__device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int ld, int md, int max_sweeps,
-                                       float* __restrict__ rot) {
-  const int nthreads = blockDim.x;
-  for (int e = threadIdx.x; e < md * md; e += nthreads) {
+// Symmetric eigen-decomposition of the leading md x md block of H (row stride ld, md even): parallel-order
+// two-sided Jacobi.  Every round the md/2 rotations of a round-robin pairing are computed once (one thread each),
+// then every 2 x 2 block of J^T H J and every row pair of S J is updated in place by its own thread.  On exit H's
+// diagonal holds the eigenvalues and Sm (same stride) the eigenvectors (columns).  A sweep whose rotations were
+// all below 1e-4 (relative) ends the iteration: convergence is quadratic.
+// WARP = true: run by one warp (barriers are __syncwarp); false: by the whole CTA.
+template <bool WARP>
+__device__ __forceinline__ void jacobi_impl(float* __restrict__ H, float* __restrict__ Sm, int ld, int md,
+                                            int max_sweeps, float* __restrict__ rot) {
+  const int nthreads = WARP ? 32 : blockDim.x;
+  const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  auto sync = [&]() {
+    if constexpr (WARP) __syncwarp();
+    else __syncthreads();
+  };
+  for (int e = tid; e < md * md; e += nthreads) {
     const int a = e / md, b = e - a * md;
     Sm[a * ld + b] = a == b ? 1.f : 0.f;
     if (a < b) {
@@ -565,14 +651,14 @@ __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict_
       H[b * ld + a] = v;
     }
   }
-  __syncthreads();
+  sync();
   const int half = md >> 1;
   const int nb = half * half, ns = md * half;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     bool big = false;
     for (int r = 0; r < md - 1; ++r) {
-      if (threadIdx.x < half) {
-        const int tq = threadIdx.x;
+      if (tid < half) {
+        const int tq = tid;
         int p, q;
         if (tq == 0) { p = r; q = md - 1; }
         else {
@@ -584,8 +670,8 @@ __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict_
         jacobi_rot(H[p * ld + p], H[q * ld + q], H[p * ld + q], c, s, big);
         *reinterpret_cast<float4*>(rot + 4 * tq) = make_float4(c, s, __int_as_float(p), __int_as_float(q));
       }
-      __syncthreads();
-      for (int item = threadIdx.x; item < nb + ns; item += nthreads) {
+      sync();
+      for (int item = tid; item < nb + ns; item += nthreads) {
         if (item < nb) {
           // H[P1][P2] <- J1^T H[P1][P2] J2
           const int t1 = item / half, t2 = item - t1 * half;
@@ -611,18 +697,35 @@ __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict_
           Sm[a * ld + q2] = r2.y * sp + r2.x * sq;
         }
       }
-      __syncthreads();
+      sync();
     }
-    if (!__syncthreads_or(big ? 1 : 0)) break;
+    if constexpr (WARP) {
+      if (!__any_sync(0xffffffffu, big)) break;
+    } else {
+      if (!__syncthreads_or(big ? 1 : 0)) break;
+    }
+  }
+}
+
+// Small blocks (the leading block of the final Rayleigh-Ritz step) are diagonalised by warp 0 alone: no CTA
+// barrier per round, the other warps wait once.
+__device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int ld, int md, int max_sweeps,
+                                       float* __restrict__ rot) {
+  if (md <= 8) {
+    if (threadIdx.x < 32) jacobi_impl<true>(H, Sm, ld, md, max_sweeps, rot);
+    __syncthreads();
+  } else {
+    jacobi_impl<false>(H, Sm, ld, md, max_sweeps, rot);
   }
 }
 
 // MT: 16-row tiles of the block (m <= 16 * MT).  THREADS: CTA size.
 template <int MT, int THREADS>
-__global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS) : 1) ncut_eig_kernel(const Params P) {
+__global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128 * EIG_MINB / THREADS) : 1)
+    ncut_eig_kernel(const Params P) {
   constexpr int MB = 16 * MT;
   constexpr int NWARPS = THREADS / 32;
-  constexpr int T = MT == 1 ? 4 : 2;
+  constexpr int T = MT == 1 ? EIG_T : 2;
   extern __shared__ __align__(16) float smem[];
   const Layout L = make_layout(P.N, P.m, MT, NWARPS);
   float* Ut = smem + L.Ut;
@@ -665,6 +768,7 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
 
     // ---- load: degree, start block (pad tokens and pad rows are zero)
     __syncthreads();  // the previous segment's readers of the shared arrays are done
+    PHASE_BEGIN();
     for (int i = threadIdx.x; i < npad; i += THREADS) {
       const float d = i < n ? P.deg[g.row0 + i] : 0.f;
       dg[i] = d;
@@ -680,12 +784,24 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
       Ut[c * ldt + i] = v;
       Yt[c * ldt + i] = 0.f;
     }
+    // rows of the 16-row tiles beyond `rows` exist only in the fragment-order copy
+    for (int e = threadIdx.x; e < MB * npad; e += THREADS) {
+      const int c = e / npad, i = e - c * npad;
+      float v = 0.f;
+      if (c < me && i < n && n > m) v = (c == 0) ? 1.f : hash_unit(i, c);
+      Uf[uf_index<MT>(c, i)] = v;
+    }
     __syncthreads();
 
-    // ---- D-orthonormalise the start block
-    weighted_grams<NWARPS>(Ut, Ut, dg, n, m, ldt, rows, Gs, Hs, false);
-    cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
-    orthonormalise<MT, NWARPS>(Ws, m, Ut, Ut, Uf, npad, ldt, rows);
+    // ---- D-orthonormalise the start block: only when its Rayleigh quotients are used right away (a tiny segment,
+    //      one exact step); otherwise the first product runs on the raw block and is orthonormalised after it
+    const bool ortho_start = n <= m || P.max_iter <= 1;
+    if (ortho_start) {
+      weighted_grams<NWARPS>(Ut, Ut, dg, n, m, ldt, rows, Gs, Hs, false);
+      cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
+      orthonormalise<MT, NWARPS>(Ws, m, Ut, Ut, Uf, npad, ldt, rows);
+    }
+    PHASE_END(PH_INIT);
 
     int it = 0;
     const float tol2 = P.tol * P.tol;
@@ -694,13 +810,34 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
       if (it <= P.fast_iters) matvec<MT, T, false, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
       else matvec<MT, T, true, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
       __syncthreads();
+      PHASE_END(PH_MATVEC);
       const bool last = it >= P.max_iter || n <= m;  // n <= m: span(U) is the whole space, one step is exact
       // ---- G = Y^T D Y, H = U^T D Y (U is D-orthonormal) and the trigger: for each wanted column j
       //        |y_j - U h_j|_D^2 + sum_{a >= kk} H[a][j]^2   =   residual of the Ritz problem on the leading columns
       weighted_grams<NWARPS>(Ut, Yt, dg, n, m, ldt, rows, Gs, Hs, true);
+      PHASE_END(PH_GRAMS);
       const bool scheduled = last || (it % P.rr_every) == 0;
       bool fired = false;
-      if (!scheduled && it >= 2 && it > P.fast_iters) {
+      bool test = !scheduled && it >= 2 && it > P.fast_iters;
+      if (test) {
+        // cheap screen: |y_c - U h_c|_D^2 + coupling = G_cc - sum_{a < kk} H_ac^2 up to rounding (U is D-orthonormal);
+        // far above the tolerance (and the rounding floor) means not converged -- skip the explicit residuals
+        if (threadIdx.x == 0) {
+          float worst = 0.f;
+          for (int c = 0; c < kk; ++c) {
+            const float gcc = Gs[c * ld + c];
+            float v = gcc;
+            for (int a = 0; a < kk; ++a) v = fmaf(-Hs[a * ld + c], Hs[a * ld + c], v);
+            v -= 64.f * tol2 + 8e-6f * gcc;
+            if (Hs[c * ld + c] >= P.lam_floor) worst = fmaxf(worst, v);
+          }
+          misc[2] = worst > 0.f ? 0.f : 1.f;
+        }
+        __syncthreads();
+        test = misc[2] != 0.f;
+        __syncthreads();
+      }
+      if (test) {
         span_residuals<MT, NWARPS>(Hs, m, Ut, Yt, dg, kk, npad, ldt, rows, colred, res);
         if (threadIdx.x == 0) {
           float worst = 0.f;
@@ -713,17 +850,19 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
         }
         __syncthreads();
         fired = misc[2] != 0.f;
+        PHASE_END(PH_TRIGGER);
       }
       bool rotated = false;
       if (scheduled || fired) {
         // ---- Rayleigh-Ritz: the whole block (scheduled; a few sweeps unless it is the last step), or only the
         //      leading columns once they span an invariant subspace (trigger; to full accuracy)
-        int md = m, sweeps = last ? 12 : 3;
+        int md = m, sweeps = last ? 12 : EIG_SWEEPS;
         if (!scheduled) {
           const int mdb = (kk + 1) & ~1;
           if (mdb <= me) { md = mdb; sweeps = 12; }
         }
         jacobi(Hs, Ss, ld, md, sweeps, rot);
+        PHASE_END(PH_JACOBI);
         if (threadIdx.x < m) {
           const int a = threadIdx.x;
           const float ta = Hs[a * ld + a];
@@ -754,17 +893,24 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
           misc[1] = worst;
         }
         __syncthreads();
+        PHASE_END(PH_ROTATE);
         if (last || misc[1] <= tol2) break;
         rotated = true;
       }
       // ---- U = orth_D(Y)
-      if (rotated) weighted_grams<NWARPS>(Ut, Yt, dg, n, m, ldt, rows, Gs, Hs, false);  // G of the rotated Y
+      if (rotated) {
+        weighted_grams<NWARPS>(Ut, Yt, dg, n, m, ldt, rows, Gs, Hs, false);  // G of the rotated Y
+        PHASE_END(PH_GRAMS);
+      }
       const float piv = cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
+      PHASE_END(PH_CHOL);
       orthonormalise<MT, NWARPS>(Ws, m, Yt, Ut, Uf, npad, ldt, rows);
+      PHASE_END(PH_ORTH);
       if (piv < 0.05f) {
         weighted_grams<NWARPS>(Ut, Ut, dg, n, m, ldt, rows, Gs, Hs, false);
         cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
         orthonormalise<MT, NWARPS>(Ws, m, Ut, Ut, Uf, npad, ldt, rows);
+        PHASE_END(PH_ORTH);
       }
     }
 
@@ -798,6 +944,7 @@ __global__ void __launch_bounds__(THREADS, (512 / THREADS) > 0 ? (512 / THREADS)
       Vout[e] = c < me ? Ut[c * ldt + i] * sqrtf(dg[i]) * res[c] : 0.f;
     }
     if (P.iters && threadIdx.x == 0) P.iters[s] = it;
+    PHASE_END(PH_OUTPUT);
   }
 }
 
@@ -830,6 +977,19 @@ static int launch_threads(const Params& P, cudaStream_t stream) {
 }  // namespace eig
 }  // namespace msvit
 
+#ifdef EIG_PROFILE
+extern "C" int msvit_eig_profile(unsigned long long* host_out, int reset) {
+  using namespace msvit::eig;
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, g_phase_cycles, sizeof(unsigned long long) * PH_COUNT);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (reset) {
+    unsigned long long z[PH_COUNT] = {};
+    e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return static_cast<int>(e);
+}
+#endif
+
 extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32_t* iters,
                               int64_t total_rows, int S, int N, int k, int block, int max_iter, float tol,
                               float lam_floor, const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream_) {
@@ -847,8 +1007,8 @@ extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float*
   P.A = A; P.deg = deg; P.V = V; P.lam = lam; P.iters = iters;
   P.seg_off = seg_off; P.a_off = a_off;
   P.S = S; P.N = N; P.k = k; P.m = block;
-  P.max_iter = max_iter; P.rr_every = 3; P.tol = tol; P.lam_floor = lam_floor;
-  P.fast_iters = 0;
+  P.max_iter = max_iter; P.rr_every = EIG_RR_EVERY; P.tol = tol; P.lam_floor = lam_floor;
+  P.fast_iters = EIG_FAST_ITERS;
   if (block <= 16) return launch_threads<1>(P, stream);
   return launch_threads<2>(P, stream);
 }
