@@ -49,7 +49,7 @@
 #define EIG_RR_EVERY 3
 #endif
 #ifndef EIG_SWEEPS     // Jacobi sweeps of a scheduled (not final) Rayleigh-Ritz step
-#define EIG_SWEEPS 3
+#define EIG_SWEEPS 2
 #endif
 #ifndef EIG_FAST_ITERS // leading products done in a single TF32 pass
 #define EIG_FAST_ITERS 0
@@ -167,10 +167,19 @@ __device__ __forceinline__ int uf_index(int c, int j) {
   return ((kb * MT + mt) * 2 + ks) * 128 + (cg * 4 + tt) * 4 + kh * 2 + half;
 }
 
-// One 16-column block of the product for TC row tiles: acc[q] += Ufrag(kb) * x[q]^T.
+// One 16-column block of the product for TC row tiles: acc[q] += Ufrag(kb) * x[q]^T.  The warp issues in order, so
+// the MMAs are emitted round-robin over the TC independent accumulators (a dependent MMA would stall the issue slot
+// for its whole latency).
 template <int MT, int TC, bool FULL>
 __device__ __forceinline__ void matvec_block(float (&acc)[TC][MT][4], const float4 (&x)[TC],
                                              const float* __restrict__ uf, int kb) {
+  uint32_t xl[TC][4];
+  if constexpr (FULL) {
+#pragma unroll
+    for (int q = 0; q < TC; ++q) {
+      xl[q][0] = lo_bits(x[q].x); xl[q][1] = lo_bits(x[q].y); xl[q][2] = lo_bits(x[q].z); xl[q][3] = lo_bits(x[q].w);
+    }
+  }
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const float4 ua = *reinterpret_cast<const float4*>(uf + ((kb * MT + mt) * 2) * 128);
@@ -178,18 +187,20 @@ __device__ __forceinline__ void matvec_block(float (&acc)[TC][MT][4], const floa
     uint32_t uah[4], ual[4], ubh[4], ubl[4];
     split4(ua, uah, ual);
     split4(ub, ubh, ubl);
+    if constexpr (FULL) {
 #pragma unroll
-    for (int q = 0; q < TC; ++q) {
-      const float4 c = x[q];
-      if constexpr (FULL) {
-        mma_tf32(acc[q][mt], ual, __float_as_uint(c.x), __float_as_uint(c.y));
-        mma_tf32(acc[q][mt], uah, lo_bits(c.x), lo_bits(c.y));
-        mma_tf32(acc[q][mt], ubl, __float_as_uint(c.z), __float_as_uint(c.w));
-        mma_tf32(acc[q][mt], ubh, lo_bits(c.z), lo_bits(c.w));
-      }
-      mma_tf32(acc[q][mt], uah, __float_as_uint(c.x), __float_as_uint(c.y));
-      mma_tf32(acc[q][mt], ubh, __float_as_uint(c.z), __float_as_uint(c.w));
+      for (int q = 0; q < TC; ++q) mma_tf32(acc[q][mt], ual, __float_as_uint(x[q].x), __float_as_uint(x[q].y));
+#pragma unroll
+      for (int q = 0; q < TC; ++q) mma_tf32(acc[q][mt], uah, xl[q][0], xl[q][1]);
+#pragma unroll
+      for (int q = 0; q < TC; ++q) mma_tf32(acc[q][mt], ubl, __float_as_uint(x[q].z), __float_as_uint(x[q].w));
+#pragma unroll
+      for (int q = 0; q < TC; ++q) mma_tf32(acc[q][mt], ubh, xl[q][2], xl[q][3]);
     }
+#pragma unroll
+    for (int q = 0; q < TC; ++q) mma_tf32(acc[q][mt], uah, __float_as_uint(x[q].x), __float_as_uint(x[q].y));
+#pragma unroll
+    for (int q = 0; q < TC; ++q) mma_tf32(acc[q][mt], ubh, __float_as_uint(x[q].z), __float_as_uint(x[q].w));
   }
 }
 
@@ -210,6 +221,9 @@ __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int ld
   for (int q = 0; q < TC; ++q) {
     const int r = min(8 * (tile0 + q) + g, n - 1);
     off[q] = static_cast<uint32_t>(r) * static_cast<uint32_t>(lda) + 4u * t;
+#ifdef EIG_FAKE_A  // experiment: every lane streams row 0 (always cached)
+    off[q] = 4u * t;
+#endif
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -304,24 +318,51 @@ __device__ __forceinline__ void weighted_grams(const float* __restrict__ Pt, con
     const float* at = (mat == 0 ? Qt : Pt) + (16 * mt + g) * ldt + 4 * t;
     const float* bt = Qt + (8 * nt + g) * ldt + 4 * t;
     const float* dp = dg + 4 * t;
-    float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int kb = 0; kb < KB; ++kb) {
-      const float4 a0 = *reinterpret_cast<const float4*>(at + 16 * kb);
-      const float4 a1 = v1 ? *reinterpret_cast<const float4*>(at + 8 * ldt + 16 * kb) : zero4;
-      float4 b = *reinterpret_cast<const float4*>(bt + 16 * kb);
-      const float4 d = *reinterpret_cast<const float4*>(dp + 16 * kb);
-      b.x *= d.x; b.y *= d.y; b.z *= d.z; b.w *= d.w;
-      const uint32_t ah0[4] = {hi_bits(a0.x), hi_bits(a1.x), hi_bits(a0.y), hi_bits(a1.y)};
-      const uint32_t al0[4] = {lo_bits(a0.x), lo_bits(a1.x), lo_bits(a0.y), lo_bits(a1.y)};
-      const uint32_t ah1[4] = {hi_bits(a0.z), hi_bits(a1.z), hi_bits(a0.w), hi_bits(a1.w)};
-      const uint32_t al1[4] = {lo_bits(a0.z), lo_bits(a1.z), lo_bits(a0.w), lo_bits(a1.w)};
-      mma_tf32(lo, al0, __float_as_uint(b.x), __float_as_uint(b.y));
-      mma_tf32(lo, ah0, lo_bits(b.x), lo_bits(b.y));
-      mma_tf32(lo, al1, __float_as_uint(b.z), __float_as_uint(b.w));
-      mma_tf32(lo, ah1, lo_bits(b.z), lo_bits(b.w));
-      mma_tf32(hi, ah0, __float_as_uint(b.x), __float_as_uint(b.y));
-      mma_tf32(hi, ah1, __float_as_uint(b.z), __float_as_uint(b.w));
+    // six independent accumulators (k-block parity x {lo*hi, hi*lo, hi*hi}): consecutive MMAs never depend
+    float ac[2][3][4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ac[p][c][e] = 0.f;
+    for (int kb0 = 0; kb0 < KB; kb0 += 2) {
+      uint32_t ah0[2][4], al0[2][4], ah1[2][4], al1[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int kb = kb0 + p;
+        const bool in = kb < KB;  // warp-uniform
+        const float4 a0 = in ? *reinterpret_cast<const float4*>(at + 16 * kb) : zero4;
+        const float4 a1 = (in && v1) ? *reinterpret_cast<const float4*>(at + 8 * ldt + 16 * kb) : zero4;
+        float4 b = in ? *reinterpret_cast<const float4*>(bt + 16 * kb) : zero4;
+        const float4 d = in ? *reinterpret_cast<const float4*>(dp + 16 * kb) : zero4;
+        b.x *= d.x; b.y *= d.y; b.z *= d.z; b.w *= d.w;
+        ah0[p][0] = hi_bits(a0.x); ah0[p][1] = hi_bits(a1.x); ah0[p][2] = hi_bits(a0.y); ah0[p][3] = hi_bits(a1.y);
+        al0[p][0] = lo_bits(a0.x); al0[p][1] = lo_bits(a1.x); al0[p][2] = lo_bits(a0.y); al0[p][3] = lo_bits(a1.y);
+        ah1[p][0] = hi_bits(a0.z); ah1[p][1] = hi_bits(a1.z); ah1[p][2] = hi_bits(a0.w); ah1[p][3] = hi_bits(a1.w);
+        al1[p][0] = lo_bits(a0.z); al1[p][1] = lo_bits(a1.z); al1[p][2] = lo_bits(a0.w); al1[p][3] = lo_bits(a1.w);
+        bh[p][0] = __float_as_uint(b.x); bh[p][1] = __float_as_uint(b.y);
+        bh[p][2] = __float_as_uint(b.z); bh[p][3] = __float_as_uint(b.w);
+        bl[p][0] = lo_bits(b.x); bl[p][1] = lo_bits(b.y); bl[p][2] = lo_bits(b.z); bl[p][3] = lo_bits(b.w);
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        mma_tf32(ac[p][0], al0[p], bh[p][0], bh[p][1]);
+        mma_tf32(ac[p][1], ah0[p], bl[p][0], bl[p][1]);
+        mma_tf32(ac[p][2], ah0[p], bh[p][0], bh[p][1]);
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        mma_tf32(ac[p][0], al1[p], bh[p][2], bh[p][3]);
+        mma_tf32(ac[p][1], ah1[p], bl[p][2], bl[p][3]);
+        mma_tf32(ac[p][2], ah1[p], bh[p][2], bh[p][3]);
+      }
+    }
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      lo[e] = (ac[0][0][e] + ac[1][0][e]) + (ac[0][1][e] + ac[1][1][e]);
+      hi[e] = ac[0][2][e] + ac[1][2][e];
     }
     float* out = mat == 0 ? Gs : Hs;
     const int r0 = 16 * mt + g, r1 = r0 + 8, c0 = 8 * nt + 2 * t, c1 = c0 + 1;
@@ -362,33 +403,45 @@ __device__ __forceinline__ void load_wfrag(WFrag<MT>& w, const float* __restrict
   }
 }
 
-// acc[mt] = fragment of (W X^T)[16mt .. 16mt+15][i0 .. i0+7]
-template <int MT>
+// acc[u][mt] = fragment of (W X^T)[16mt .. 16mt+15][i0[u] .. i0[u]+7] for NU token tiles at once.  MMAs are issued
+// round-robin over 3 * NU * MT independent accumulators (lo*hi, hi*lo, hi*hi per tile).
+template <int MT, int NU>
 __device__ __forceinline__ void tile_product(const WFrag<MT>& w, const float* __restrict__ Xt, int ldt, int rows,
-                                             int i0, float (&acc)[MT][4]) {
+                                             const int (&i0)[NU], float (&acc)[NU][MT][4]) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  float lo[MT][4];
+  float l1[NU][MT][4], l2[NU][MT][4];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+  for (int u = 0; u < NU; ++u)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[mt][e] = lo[mt][e] = 0.f;
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[u][mt][e] = l1[u][mt][e] = l2[u][mt][e] = 0.f;
 #pragma unroll
   for (int ks = 0; ks < 2 * MT; ++ks) {
     const int ra = 8 * ks + t, rb = ra + 4;
-    const float x0 = ra < rows ? Xt[ra * ldt + i0 + g] : 0.f;
-    const float x1 = rb < rows ? Xt[rb * ldt + i0 + g] : 0.f;
+    float x0[NU], x1[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      x0[u] = ra < rows ? Xt[ra * ldt + i0[u] + g] : 0.f;
+      x1[u] = rb < rows ? Xt[rb * ldt + i0[u] + g] : 0.f;
+    }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      mma_tf32(lo[mt], w.lo[mt][ks], __float_as_uint(x0), __float_as_uint(x1));
-      mma_tf32(lo[mt], w.hi[mt][ks], lo_bits(x0), lo_bits(x1));
-      mma_tf32(acc[mt], w.hi[mt][ks], __float_as_uint(x0), __float_as_uint(x1));
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_tf32(l1[u][mt], w.lo[mt][ks], __float_as_uint(x0[u]), __float_as_uint(x1[u]));
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_tf32(l2[u][mt], w.hi[mt][ks], lo_bits(x0[u]), lo_bits(x1[u]));
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mma_tf32(acc[u][mt], w.hi[mt][ks], __float_as_uint(x0[u]), __float_as_uint(x1[u]));
     }
   }
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+  for (int u = 0; u < NU; ++u)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[mt][e] += lo[mt][e];
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[u][mt][e] += l1[u][mt][e] + l2[u][mt][e];
 }
 
 // Per-row sums held as fragment partials rs[mt][h] (row 16mt + 8h + g, summed over this lane's tokens):
@@ -426,19 +479,23 @@ __device__ __forceinline__ void orthonormalise(const float* __restrict__ W, int 
   const int g = lane >> 2, t = lane & 3;
   WFrag<MT> w;
   load_wfrag<MT>(w, W, m + 1, m, m, false);
-  for (int tile = warp; tile < (npad >> 3); tile += NWARPS) {
-    const int i0 = 8 * tile;
-    float acc[MT][4];
-    tile_product<MT>(w, Xt, ldt, rows, i0, acc);
-    const int j = i0 + 2 * t;
-    const int kb = j >> 4, tt = (j >> 2) & 3, ks = (j >> 1) & 1;
+  // two 8-token tiles per step (npad is a multiple of 16): tile pairs are dealt round-robin to the warps
+  for (int pair = warp; pair < (npad >> 4); pair += NWARPS) {
+    const int i0[2] = {16 * pair, 16 * pair + 8};
+    float acc[2][MT][4];
+    tile_product<MT, 2>(w, Xt, ldt, rows, i0, acc);
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int r0 = 16 * mt + g, r1 = r0 + 8;
-      if (r0 < rows) *reinterpret_cast<float2*>(Ut + r0 * ldt + j) = make_float2(acc[mt][0], acc[mt][1]);
-      if (r1 < rows) *reinterpret_cast<float2*>(Ut + r1 * ldt + j) = make_float2(acc[mt][2], acc[mt][3]);
-      *reinterpret_cast<float4*>(Uf + ((kb * MT + mt) * 2 + ks) * 128 + (g * 4 + tt) * 4) =
-          make_float4(acc[mt][0], acc[mt][2], acc[mt][1], acc[mt][3]);
+    for (int u = 0; u < 2; ++u) {
+      const int j = i0[u] + 2 * t;
+      const int kb = j >> 4, tt = (j >> 2) & 3, ks = (j >> 1) & 1;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+        if (r0 < rows) *reinterpret_cast<float2*>(Ut + r0 * ldt + j) = make_float2(acc[u][mt][0], acc[u][mt][1]);
+        if (r1 < rows) *reinterpret_cast<float2*>(Ut + r1 * ldt + j) = make_float2(acc[u][mt][2], acc[u][mt][3]);
+        *reinterpret_cast<float4*>(Uf + ((kb * MT + mt) * 2 + ks) * 128 + (g * 4 + tt) * 4) =
+            make_float4(acc[u][mt][0], acc[u][mt][2], acc[u][mt][1], acc[u][mt][3]);
+      }
     }
   }
   __syncthreads();
@@ -465,9 +522,12 @@ __device__ __forceinline__ void rotate(const float* __restrict__ W, int m, float
     }
   for (int tile = warp; tile < (npad >> 3); tile += NWARPS) {
     const int i0 = 8 * tile;
-    float au[MT][4], ay[MT][4];
-    tile_product<MT>(w, Ut, ldt, rows, i0, au);
-    tile_product<MT>(w, Yt, ldt, rows, i0, ay);
+    const int i1[1] = {i0};
+    float au1[1][MT][4], ay1[1][MT][4];
+    tile_product<MT, 1>(w, Ut, ldt, rows, i1, au1);
+    tile_product<MT, 1>(w, Yt, ldt, rows, i1, ay1);
+    float (&au)[MT][4] = au1[0];
+    float (&ay)[MT][4] = ay1[0];
     const int j = i0 + 2 * t;
     const float2 d = *reinterpret_cast<const float2*>(dg + j);
 #pragma unroll
@@ -505,8 +565,10 @@ __device__ __forceinline__ void span_residuals(const float* __restrict__ Hs, int
   for (int mt = 0; mt < MT; ++mt) rs[mt][0] = rs[mt][1] = 0.f;
   for (int tile = warp; tile < (npad >> 3); tile += NWARPS) {
     const int i0 = 8 * tile;
-    float acc[MT][4];
-    tile_product<MT>(w, Ut, ldt, rows, i0, acc);
+    const int i1[1] = {i0};
+    float acc1[1][MT][4];
+    tile_product<MT, 1>(w, Ut, ldt, rows, i1, acc1);
+    float (&acc)[MT][4] = acc1[0];
     const int j = i0 + 2 * t;
     const float2 d = *reinterpret_cast<const float2*>(dg + j);
 #pragma unroll
@@ -822,16 +884,18 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
       if (test) {
         // cheap screen: |y_c - U h_c|_D^2 + coupling = G_cc - sum_{a < kk} H_ac^2 up to rounding (U is D-orthonormal);
         // far above the tolerance (and the rounding floor) means not converged -- skip the explicit residuals
-        if (threadIdx.x == 0) {
-          float worst = 0.f;
-          for (int c = 0; c < kk; ++c) {
+        if (warp == 0) {
+          float v = 0.f;
+          for (int c = lane; c < kk; c += 32) {
             const float gcc = Gs[c * ld + c];
-            float v = gcc;
-            for (int a = 0; a < kk; ++a) v = fmaf(-Hs[a * ld + c], Hs[a * ld + c], v);
-            v -= 64.f * tol2 + 8e-6f * gcc;
-            if (Hs[c * ld + c] >= P.lam_floor) worst = fmaxf(worst, v);
+            float e = gcc;
+            for (int a = 0; a < kk; ++a) e = fmaf(-Hs[a * ld + c], Hs[a * ld + c], e);
+            e -= 64.f * tol2 + 8e-6f * gcc;
+            if (Hs[c * ld + c] >= P.lam_floor) v = fmaxf(v, e);
           }
-          misc[2] = worst > 0.f ? 0.f : 1.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+          if (lane == 0) misc[2] = v > 0.f ? 0.f : 1.f;
         }
         __syncthreads();
         test = misc[2] != 0.f;
@@ -962,7 +1026,10 @@ static int launch(const Params& P, cudaStream_t stream) {
   if (per_sm < 1) per_sm = 1;
   // one CTA per segment while that is at most a few waves, else a persistent grid-stride loop
   const long long cap = 16LL * per_sm * sm_count();
-  const int grid = static_cast<int>(P.S < cap ? P.S : cap);
+  int grid = static_cast<int>(P.S < cap ? P.S : cap);
+#ifdef EIG_MAX_GRID
+  if (grid > EIG_MAX_GRID) grid = EIG_MAX_GRID;
+#endif
   ncut_eig_kernel<MT, THREADS><<<grid, THREADS, smem, stream>>>(P);
   return cuda_status(cudaGetLastError());
 }
