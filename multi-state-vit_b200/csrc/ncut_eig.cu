@@ -52,7 +52,7 @@
 #define EIG_SWEEPS 2
 #endif
 #ifndef EIG_FAST_ITERS // leading products done in a single TF32 pass
-#define EIG_FAST_ITERS 0
+#define EIG_FAST_ITERS 2
 #endif
 
 namespace msvit {
@@ -869,7 +869,8 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
     const float tol2 = P.tol * P.tol;
     while (true) {
       ++it;
-      if (it <= P.fast_iters) matvec<MT, T, false, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
+      // single-pass products only where later full-precision steps follow (not for the one exact step of a tiny segment)
+      if (it <= P.fast_iters && n > m && it < P.max_iter) matvec<MT, T, false, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
       else matvec<MT, T, true, NWARPS>(Ag, lda, n, Uf, Yt, dinv, ldt, rows);
       __syncthreads();
       PHASE_END(PH_MATVEC);
