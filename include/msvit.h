@@ -113,6 +113,30 @@ int msvit_gather_rows(const void* x, int x_dtype, const int32_t* perm, void* xs,
 int msvit_compose_labels(const int32_t* labels_sorted, const int32_t* n_child, const int32_t* perm,
                          const int32_t* seg_off, int64_t* child, int B, int N, int P, msvit_stream_t stream);
 
+/* Dataset-level k-means over a row shard of a feature matrix (one Lloyd iteration = assign, sort, accumulate,
+ * [all-reduce of `packed` by the caller when rows are sharded over GPUs], finalize).
+ * Replaces the flattened-batch clustering of model/clustering/modeling_spectral.py:254-256 and the
+ * KMeans(n_clusters).fit_predict call sites (:90, :130-133) at dataset scale (BASELINE.json configs[4]).
+ *
+ * msvit_gkm_assign: labels[i] = argmin_c |c|^2 - 2 x_i.c (ties -> lowest c), on the tensor cores.
+ *   x [n, D] and centroids_op [k, D] share x_dtype (MSVIT_F32 is read as TF32, rounded to nearest);
+ *   labels [n] int32; best [n] = the minimal score (may be NULL).  D*elsize % 16 == 0.
+ * msvit_gkm_sort: stable counting sort of row ids by label: perm [n] (rows grouped by label, ascending row id
+ *   inside a label), seg_off [k+1].  workspace: msvit_gkm_workspace_bytes(n, k) bytes.  k <= 12000.
+ * msvit_gkm_accumulate: packed [k, D+1] fp32: columns [0, D) = sum of the member rows (fixed order, no atomics),
+ *   column D = member count.
+ * msvit_gkm_finalize: centroids [k, D] fp32 (in/out) = sum / count where count > 0 (an empty cluster keeps its
+ *   centre); centroids_op [k, D] in op_dtype (may be NULL) = the tensor-core operand copy. */
+int msvit_gkm_assign(const void* x, int x_dtype, const void* centroids_op, int32_t* labels, float* best, int64_t n,
+                     int k, int D, msvit_stream_t stream);
+size_t msvit_gkm_workspace_bytes(int64_t n, int k);
+int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* perm, int32_t* seg_off, void* workspace,
+                   size_t workspace_bytes, msvit_stream_t stream);
+int msvit_gkm_accumulate(const void* x, int x_dtype, const int32_t* perm, const int32_t* seg_off, float* packed,
+                         int64_t n, int k, int D, msvit_stream_t stream);
+int msvit_gkm_finalize(const float* packed, float* centroids, void* centroids_op, int op_dtype, int k, int D,
+                       msvit_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

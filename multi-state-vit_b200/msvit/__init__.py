@@ -8,8 +8,9 @@ All compute runs in libmsvit.so (csrc/, C ABI in include/msvit.h); there is no C
 from . import _lib
 from .clustering import (CLUSTERING_CLASSES, ClusteringConfig, ClusteringModule, SpectralClustering,
                          SpectralClusteringConfig)
+from .global_kmeans import GlobalKMeansPlan, GlobalKMeansResult, global_kmeans
 from .functional import ClusterOutput, ClusterPlan, HostClusterer, HostResult, affinity, cluster_tokens, kmeans, ncut_eig, pool
 
 __all__ = ["CLUSTERING_CLASSES", "ClusteringConfig", "ClusteringModule", "SpectralClustering",
            "SpectralClusteringConfig", "ClusterOutput", "ClusterPlan", "HostClusterer", "HostResult", "affinity", "cluster_tokens", "kmeans", "ncut_eig", "pool",
-           "_lib"]
+           "GlobalKMeansPlan", "GlobalKMeansResult", "global_kmeans", "_lib"]

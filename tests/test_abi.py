@@ -53,6 +53,15 @@ def test_argument_checks_fire_before_any_cuda_call(lib):
     assert lib.msvit_pool(p16, 0, None, p16, p16, 1, 8, 8, 2, None) == -1
     assert lib.msvit_pool(p16, 0, p16, p16, p16, 1, 8, 8, 0, None) == -2
     assert lib.msvit_compose_labels(p16, p16, None, None, p16, 1, 8, 2, None) == -2  # P > 1 needs seg_off
+    assert lib.msvit_gkm_assign(p16, 0, None, p16, None, 8, 2, 8, None) == -1
+    assert lib.msvit_gkm_assign(p16, 0, p16, p16, None, 8, 2, 3, None) == -3           # row stride % 16
+    assert lib.msvit_gkm_assign(p16, 5, p16, p16, None, 8, 2, 8, None) == -4
+    assert lib.msvit_gkm_sort(p16, 8, 2, p16, p16, p16, 0, None) == -5                 # workspace too small
+    assert lib.msvit_gkm_sort(p16, 8, 2, p16, p16, None, 64, None) == -1
+    assert lib.msvit_gkm_accumulate(p16, 1, p16, p16, p16, 8, 2, 12, None) == -2       # D % 8 for bf16
+    assert lib.msvit_gkm_finalize(p16, None, None, 0, 2, 8, None) == -1
+    assert lib.msvit_gkm_workspace_bytes(4096, 10) == 2 * 10 * 4
+    assert lib.msvit_gkm_assign(p16, 0, p16, p16, None, 0, 2, 8, None) == 0
     # empty batches are a no-op
     assert lib.msvit_affinity_degree(p16, 0, None, p16, 0, 0, 8, 8, 0, 3.0, 1.0, None, None, None) == 0
     assert lib.msvit_pool(p16, 0, p16, p16, p16, 0, 8, 8, 2, None) == 0
