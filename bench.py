@@ -77,7 +77,7 @@ def stage_work(B, N, D, K, k, esz):
     w = {}
     # affinity: read X once, write A (fp32, padded rows) and deg; flops = Gram 2 N^2 D
     w["affinity"] = {"bytes": B * (esz * N * D + 4 * N * lda + 4 * N), "flops": 2.0 * B * N * N * D}
-    # eigensolver: read A and deg once (A is then shared-memory resident), write V and lambda
+    # eigensolver: compulsory traffic = A and deg once, V and lambda out (A is re-read from L2 every iteration)
     w["eig"] = {"bytes": B * (4 * N * lda + 4 * N + 4 * N * k + 4 * k), "flops": 0.0}
     # k-means: read V, lambda, deg; write labels (int32) and the child count
     w["kmeans"] = {"bytes": B * (4 * N * k + 4 * k + 4 * N + 4 * N + 4), "flops": 0.0}
@@ -353,13 +353,130 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ C5: dataset-level k-means
+C5_METRIC = "rows/sec per Lloyd iteration, global k-means k=1000 over 1M x 768 features (BASELINE.json configs[4])"
+
+
+def run_c5(args):
+    """`--config C5`: one step = one Lloyd iteration (assign -> sort -> accumulate -> all-reduce -> finalize) over
+    all 1 000 000 rows, sharded over the ranks (strong scaling: the total is fixed); the only collective is the
+    all-reduce of the packed [k, D+1] sums|counts buffer (3.08 MB) over NCCL."""
+    import torch.distributed as dist
+    import msvit
+    from msvit.global_kmeans import GlobalKMeansPlan, broadcast_init, global_kmeans
+    from msvit.sharding import max_over_ranks, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    msvit._lib.load()
+    n_total, D, k = args.c5_rows, 768, 1000
+    first, n = shard_bounds(n_total, rank, world)
+    dtype = torch.bfloat16 if args.dtype != "float32" or True else torch.float32
+    # planted mixture (SURVEY.md 8d): centres1000[label] + 0.5 randn, seed 1212; every rank generates its own rows
+    g = torch.Generator(device=dev).manual_seed(1212)
+    centres = torch.randn(k, D, generator=g, device=dev)
+    g.manual_seed(1212 + 7919 * (rank + 1))
+    x = torch.empty(n, D, dtype=dtype, device=dev)
+    for r0 in range(0, n, 1 << 16):
+        r1 = min(n, r0 + (1 << 16))
+        lab = torch.randint(0, k, (r1 - r0,), generator=g, device=dev)
+        x[r0:r1] = (centres[lab] + 0.5 * torch.randn(r1 - r0, D, generator=g, device=dev)).to(dtype)
+    plan = GlobalKMeansPlan(n, D, k, dtype, dev)
+    plan.set_centroids(broadcast_init(x, k))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    names = ("assign", "sort", "accumulate", "allreduce", "finalize")
+
+    def step(ev=None):
+        packed = plan.local_step(x, events=ev)
+        if world > 1:
+            dist.all_reduce(packed)
+        if ev is not None:
+            ev[4].record()
+        plan.finalize(packed)
+        if ev is not None:
+            ev[5].record()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for s in range(args.steps):
+        step(events[s])
+    t1.record()
+    barrier()
+    ms_total = max_over_ranks(t0.elapsed_time(t1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in events) / args.steps for i, nm in enumerate(names)}
+
+    # end to end: the public call on HOST features (H2D of the shard, `steps` iterations, D2H of centroids and labels)
+    host = x.cpu().pin_memory()
+    barrier()
+    w0 = time.perf_counter()
+    res = global_kmeans(host.to(dev, non_blocking=True), k, args.steps, init=plan.centroids.clone())
+    cent_h, lab_h = res.centroids.cpu(), res.labels.cpu()
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - w0), dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    ms_step = ms_total / args.steps
+    flops = 2.0 * n * k * D
+    ach = flops / stage_ms["assign"] / 1e9
+    line = {
+        "metric": C5_METRIC, "value": round(n_total / ms_step * 1e3, 1), "unit": "rows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"C5: {n_total} x {D} bf16 features, k={k}, rows sharded x{world} ({n} on rank 0), "
+                               f"one all-reduce of {plan.allreduce_bytes} B per iteration",
+                   "l2_policy": f"inputs larger than L2 ({n * D * 2 / 1e6:.0f} MB features per rank vs 126 MB L2)"},
+        "roofline": {"kernel": "gkm assign", "bound": "tensor", "achieved": round(ach, 1),
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(ach / peaks["bf16_tflops_sustained"], 4), "traffic": None,
+                     "peak_source": peaks["_source"] + ", sustained bf16",
+                     "share_of_step": round(stage_ms["assign"] / sum(stage_ms.values()), 3)},
+        "stages": {nm: {"ms": round(v, 4)} for nm, v in stage_ms.items()},
+        "e2e": {"value": round(n_total * args.steps / e2e_ms * 1e3, 1), "unit": "rows/s",
+                "h2d_bytes_per_step": host.numel() * 2 // args.steps,
+                "d2h_bytes_per_step": (cent_h.numel() * 4 + lab_h.numel() * 8) // args.steps,
+                "api": "msvit.global_kmeans on host features (one H2D, steps iterations, D2H of centroids + labels)"},
+        "gpu_launches": 6 * args.steps, "clocks": clocks,
+    }
+    line["stages"]["accumulate"]["GB/s"] = round((n * D * 2 + n * 4 + k * (D + 1) * 4) / stage_ms["accumulate"] / 1e6, 1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--c5-rows", type=int, default=1_000_000)
     ap.add_argument("--dtype", default="float32", choices=["float32", "bfloat16"],
                     help="dtype of the token tensor handed to the path (the reference hands fp32 hidden states)")
     ap.add_argument("--cpu-images", type=int, default=2048, help="images in the cpu_baseline sample")
@@ -371,6 +488,8 @@ def main():
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "C5":
+        run_c5(args)
     else:
         run_ours(args)
 

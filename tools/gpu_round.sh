@@ -25,6 +25,20 @@ for what in "$@"; do
       timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
       echo "benchref rc=$?"; cat gpurun_out/bench_ref.json
       ;;
+    c5)
+      timeout 900 python bench.py --config C5 --steps 10 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
+      echo "c5 rc=$?"; cat gpurun_out/bench_c5.json; tail -3 gpurun_out/bench_c5.err
+      ;;
+    c5x2)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+          bench.py --gpus 2 --config C5 --steps 10 > gpurun_out/bench_c5x2.json 2> gpurun_out/bench_c5x2.err
+      echo "c5x2 rc=$?"; cat gpurun_out/bench_c5x2.json; tail -3 gpurun_out/bench_c5x2.err
+      ;;
+    c2x2)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+          bench.py --gpus 2 > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err
+      echo "c2x2 rc=$?"; cat gpurun_out/bench_x2.json; tail -3 gpurun_out/bench_x2.err
+      ;;
     launches)
       CMD="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --cpu-images 8"
       timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
