@@ -54,6 +54,14 @@ for what in "$@"; do
           -f -o "gpurun_out/prof_${KREGEX}" $CMD > gpurun_out/ncu_full_${KREGEX}.log 2>&1
       echo "full ${KREGEX} rc=$?"
       ;;
+    fullc5:*)
+      KREGEX="${what#fullc5:}"
+      CMD="python bench.py --config C5 --steps 1 --warmup 3"
+      timeout 600 $CMD > gpurun_out/plain_fullc5.log 2>&1 &&
+      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 3 -c 1 \
+          -f -o "gpurun_out/prof_${KREGEX}" $CMD > gpurun_out/ncu_full_${KREGEX}.log 2>&1
+      echo "fullc5 ${KREGEX} rc=$?"
+      ;;
     debug:*)
       timeout 600 python tools/gpu_debug.py "${what#debug:}" 2>&1 | tee -a gpurun_out/debug.log
       ;;
