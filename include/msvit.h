@@ -137,6 +137,15 @@ int msvit_gkm_accumulate(const void* x, int x_dtype, const int32_t* perm, const 
 int msvit_gkm_finalize(const float* packed, float* centroids, void* centroids_op, int op_dtype, int k, int D,
                        msvit_stream_t stream);
 
+/* Cluster-restricted attention mask of the multi-state encoder.
+ * Replaces MultiStateViTEncoderBackbone._construct_attention_mask
+ * (model/multistate_encoder/modeling_msvitencoder.py:426-467).
+ * cluster_indices [B, N] int64 (per-image contiguous ids, as produced by the clustering module), C = the number of
+ * transmitter/receiver pairs = max cluster count over the batch (the reference reads it on the host, :451).
+ * mask [B, L, L] bytes (0/1; torch.bool layout), L = 2C + N, sequence order [T_0, R_0, .., T_{C-1}, R_{C-1}, tokens];
+ * 4-byte aligned. */
+int msvit_attention_mask(const int64_t* cluster_indices, uint8_t* mask, int B, int N, int C, msvit_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

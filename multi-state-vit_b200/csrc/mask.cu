@@ -1,0 +1,94 @@
+// Cluster-restricted attention mask of the multi-state encoder.
+//
+// Reference: MultiStateViTEncoderBackbone._construct_attention_mask(_indices)
+// (model/multistate_encoder/modeling_msvitencoder.py:426-467).  The sequence the encoder attends over is
+//     [T_0, R_0, T_1, R_1, ..., T_{C-1}, R_{C-1}, token_0 .. token_{N-1}],   C = max clusters over the batch,
+// and mask[b, q, k] is True for: two tokens of the same cluster; transmitter T_c -> tokens of cluster c; token of
+// cluster c -> receiver R_c; receiver R_r -> transmitter T_t for r, t < (clusters of image b).
+// The reference builds it with three N x N / C x N equality tensors, torch.where and index scatters; here every
+// output byte is a closed-form predicate of (q, k) and the labels, written once with 32-bit stores: HBM-write bound,
+// B * L * L bytes, L = 2C + N.
+#include "common.cuh"
+
+namespace msvit {
+namespace mask {
+
+__device__ __forceinline__ uint32_t predicate(int q, int k, int C2, int nb, const int* __restrict__ lab) {
+  const int qt = q - C2, kt = k - C2;
+  bool v;
+  if (qt >= 0) {
+    if (kt >= 0) v = lab[qt] == lab[kt];            // token -> token of the same cluster
+    else v = (k & 1) && lab[qt] == (k >> 1);        // token -> its receiver
+  } else {
+    if (kt >= 0) v = !(q & 1) && lab[kt] == (q >> 1);                     // transmitter -> its tokens
+    else v = (q & 1) && !(k & 1) && (q >> 1) < nb && (k >> 1) < nb;        // receiver -> transmitter
+  }
+  return v ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) attention_mask_kernel(const int64_t* __restrict__ cluster_indices,
+                                                             uint8_t* __restrict__ mask, int N, int C) {
+  extern __shared__ int lab[];  // [N] labels of this image, then one int for the cluster count
+  __shared__ int wmax[8];
+  const int b = blockIdx.y;
+  const int C2 = 2 * C, L = C2 + N;
+  int mx = -1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int v = static_cast<int>(cluster_indices[static_cast<size_t>(b) * N + i]);
+    lab[i] = v;
+    mx = max(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  int nb = -1;
+  for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) nb = max(nb, wmax[w]);
+  nb += 1;
+
+  const size_t total = static_cast<size_t>(L) * L;
+  uint8_t* out = mask + static_cast<size_t>(b) * total;
+  // 4 output bytes per thread where the image block allows aligned 32-bit stores
+  const bool vec = (total & 3) == 0;
+  if (vec) {
+    const size_t words = total >> 2;
+    for (size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; w < words;
+         w += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const size_t e = w << 2;
+      int q = static_cast<int>(e / L), k = static_cast<int>(e - static_cast<size_t>(q) * L);
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        word |= predicate(q, k, C2, nb, lab) << (8 * j);
+        if (++k == L) { k = 0; ++q; }
+      }
+      reinterpret_cast<uint32_t*>(out)[w] = word;
+    }
+  } else {
+    for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const int q = static_cast<int>(e / L), k = static_cast<int>(e - static_cast<size_t>(q) * L);
+      out[e] = static_cast<uint8_t>(predicate(q, k, C2, nb, lab));
+    }
+  }
+}
+
+}  // namespace mask
+}  // namespace msvit
+
+extern "C" int msvit_attention_mask(const int64_t* cluster_indices, uint8_t* mask, int B, int N, int C,
+                                    msvit_stream_t stream_) {
+  using namespace msvit;
+  if (!cluster_indices || !mask) return MSVIT_ERR_NULL;
+  if (B < 0 || N <= 0 || C <= 0 || N > 8192 || C > 4096 || B > 65535) return MSVIT_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(mask) & 3) != 0) return MSVIT_ERR_ALIGN;
+  if (B == 0) return MSVIT_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t L = static_cast<size_t>(2) * C + N;
+  const size_t per_block = 256 * 4 * 8;  // ~8 words per thread
+  int gx = static_cast<int>((L * L + per_block - 1) / per_block);
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  mask::attention_mask_kernel<<<dim3(gx, B), 256, static_cast<size_t>(N) * sizeof(int), stream>>>(cluster_indices, mask, N, C);
+  return cuda_status(cudaGetLastError());
+}

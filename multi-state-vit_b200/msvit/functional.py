@@ -246,6 +246,28 @@ def pool(x: torch.Tensor, labels: torch.Tensor, K: int):
     return ops.pool(x.contiguous(), labels.contiguous(), int(K))
 
 
+def attention_mask(cluster_indices: torch.Tensor, max_n_clusters: Optional[int] = None) -> torch.Tensor:
+    """Cluster-restricted attention mask of the multi-state encoder (modeling_msvitencoder.py:426-467):
+    cluster_indices [B, N] int64 -> bool [B, 1, L, L], L = 2C + N, sequence [T_0, R_0, .., T_{C-1}, R_{C-1}, tokens].
+
+    C = max_n_clusters; when it is not given it is read from the labels on the host, as the reference does
+    (`torch.max(cluster_indices).item() + 1`, :451) -- pass it (e.g. the plan's cluster bound) to stay asynchronous."""
+    if cluster_indices.dim() != 2 or cluster_indices.dtype != torch.int64:
+        raise ValueError("cluster_indices must be int64 [batch, tokens]")
+    if not cluster_indices.is_cuda:
+        raise RuntimeError("msvit.attention_mask runs on CUDA (sm_100a) only; there is no CPU fallback")
+    cluster_indices = cluster_indices.contiguous()
+    B, N = cluster_indices.shape
+    C = int(max_n_clusters) if max_n_clusters is not None else int(cluster_indices.max().item()) + 1
+    L = 2 * C + N
+    with torch.cuda.device(cluster_indices.device):
+        mask = torch.empty(B, 1, L, L, dtype=torch.uint8, device=cluster_indices.device)
+        st = torch.cuda.current_stream(cluster_indices.device).cuda_stream
+        _lib.check(_lib.load().msvit_attention_mask(ops._ptr(cluster_indices), ops._ptr(mask), B, N, C, st),
+                   "msvit_attention_mask")
+    return mask.view(torch.bool)
+
+
 @dataclass
 class HostResult:
     labels: torch.Tensor   # [B, N] int64, pinned host memory

@@ -261,6 +261,26 @@ def global_kmeans(feats: torch.Tensor, k: int, iters: int, init: Optional[torch.
     return C, labels, counts
 
 
+# --------------------------------------------------------------------------- attention mask of the ms-ViT caller
+def attention_mask(cluster_indices: torch.Tensor) -> torch.Tensor:
+    """Restates MultiStateViTEncoderBackbone._construct_attention_mask
+    (model/multistate_encoder/modeling_msvitencoder.py:426-467): cluster_indices [B, N] -> bool [B, 1, L, L] with
+    L = 2C + N, C = global max cluster count, sequence [T_0, R_0, .., T_{C-1}, R_{C-1}, tokens]."""
+    B, N = cluster_indices.shape
+    n_clusters = cluster_indices.max(dim=1).values + 1
+    C = int(n_clusters.max())
+    L = 2 * C + N
+    mask = torch.zeros(B, L, L, dtype=torch.bool)
+    tok = slice(2 * C, L)
+    mask[:, tok, tok] = cluster_indices[:, :, None] == cluster_indices[:, None, :]          # same cluster (:433-436)
+    member = torch.arange(C)[None, :, None] == cluster_indices[:, None, :]                    # [B, C, N] (:438-440)
+    mask[:, 0:2 * C:2, tok] = member                                                         # T_c -> its tokens (:442)
+    mask[:, tok, 1:2 * C:2] = member.transpose(1, 2)                                         # token -> R_c (:444)
+    live = torch.arange(C)[None, :] < n_clusters[:, None]                                    # [B, C] (:447-450)
+    mask[:, 1:2 * C:2, 0:2 * C:2] = live[:, :, None] & live[:, None, :]                      # R_r -> T_t (:451)
+    return mask[:, None]
+
+
 # --------------------------------------------------------------------------- helpers for tests
 def round_to_bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(x.dtype)

@@ -292,3 +292,18 @@ def test_full_size_c2_properties():
     # batch sharding equivalence: a shard clustered alone gives the same labels (no cross-image coupling)
     part = msvit.cluster_tokens(xg[512:640], ncut_dim=K, n_clusters=K, scale=default_scale(D))
     assert torch.equal(part.labels, out.labels[512:640])
+
+
+# ----------------------------------------------------------------------------------------- next row
+@pytest.mark.parametrize("shape", [(4, 196, 8), (3, 50, 5), (2, 33, 3), (1, 1024, 12), (5, 7, 7)])
+def test_attention_mask_matches_reference_restatement(shape):
+    # MultiStateViTEncoderBackbone._construct_attention_mask (msvitencoder.py:426-467): bit-exact boolean mask
+    B, N, K = shape
+    g = torch.Generator().manual_seed(N)
+    lab = torch.stack([O.canonical_relabel(torch.randint(0, max(1, K - b % 3), (N,), generator=g))[0] for b in range(B)])
+    ref = O.attention_mask(lab)
+    got = msvit.attention_mask(lab.to(DEV))
+    assert got.dtype == torch.bool and got.shape == ref.shape
+    assert torch.equal(got.cpu(), ref)
+    C = int(lab.max()) + 1
+    assert torch.equal(msvit.attention_mask(lab.to(DEV), max_n_clusters=C).cpu(), ref)   # no host read of the labels

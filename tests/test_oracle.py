@@ -150,3 +150,19 @@ def test_synthetic_generators_are_shard_consistent():
     f = planted_features(300, 8, 5, chunk=128)
     f2 = planted_features(100, 8, 5, first=150, chunk=128)
     assert torch.equal(f[150:250], f2)
+
+
+def test_attention_mask_structure():
+    # msvitencoder.py:426-467: hand-checked tiny case, 2 clusters in image 0 and 1 cluster in image 1 (C = 2)
+    lab = torch.tensor([[0, 1, 0], [0, 0, 0]])
+    m = O.attention_mask(lab)[:, 0]
+    assert m.shape == (2, 7, 7)
+    T0, R0, T1, R1, a, b, c = range(7)
+    img = m[0]
+    assert img[a, c] and img[c, a] and not img[a, b]            # tokens a, c share cluster 0
+    assert img[T0, a] and img[T0, c] and not img[T0, b] and img[T1, b]
+    assert img[a, R0] and img[b, R1] and not img[b, R0]
+    assert img[R0, T0] and img[R0, T1] and img[R1, T0] and not img[T0, R0]
+    one = m[1]
+    assert one[R0, T0] and not one[R1, T0] and not one[R0, T1]   # image 1 has a single live cluster
+    assert not one[T1].any() and one[T0, a] and one[a, R0]
