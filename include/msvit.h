@@ -73,10 +73,13 @@ int msvit_affinity_degree(const void* x, int x_dtype, float* A, float* deg, int6
  * block    subspace width m, k <= m <= MSVIT_MAX_EIG_BLOCK, m % 4 == 0
  * tol      residual tolerance |Abar v - lam v| <= tol for the k wanted pairs
  * lam_floor wanted pairs whose eigenvalue estimate is below lam_floor are exempt from the residual test
- *          (they are never clustered on when the eigenvalue threshold selects the children); 0 = none. */
+ *          (they are never clustered on when the eigenvalue threshold selects the children); 0 = none.
+ * n_converge  only the leading n_converge pairs must meet the tolerance (0 = all k): with a fixed number of
+ *          clusters K < k the k-means step reads V[:, :K] only (modeling_spectral.py:90), the remaining pairs
+ *          are returned as the current Ritz estimates. */
 int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32_t* iters, int64_t total_rows, int S,
-                   int N, int k, int block, int max_iter, float tol, float lam_floor, const int32_t* seg_off,
-                   const int64_t* a_off, msvit_stream_t stream);
+                   int N, int k, int block, int max_iter, float tol, float lam_floor, int n_converge,
+                   const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream);
 
 /* Lloyd k-means on the leading columns of the spectral embedding, per segment.
  * Replaces cuml KMeans(n_clusters).fit_predict(ncut_x[:, :n_child]) (modeling_spectral.py:90), the

@@ -84,6 +84,7 @@ struct Params {
   const int64_t* a_off;
   int S, N;
   int k, m;
+  int kconv;        // leading pairs that must meet the tolerance (<= k)
   int max_iter, rr_every;
   float tol;
   float lam_floor;  // wanted pairs whose Ritz value is below this are exempt from the residual test
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
     const float* Ag = P.A + g.a0;
     const int lda = g.lda;
     const int me = n < m ? n : m;    // effective block width
-    const int kk = k < me ? k : me;  // wanted pairs that exist
+    const int kk = P.kconv < me ? P.kconv : me;  // pairs that must converge (and exist)
     const int npad = ((n + 15) >> 4) << 4;
 
     // ---- load: degree, start block (pad tokens and pad rows are zero)
@@ -1060,12 +1061,14 @@ extern "C" int msvit_eig_profile(unsigned long long* host_out, int reset) {
 
 extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32_t* iters,
                               int64_t total_rows, int S, int N, int k, int block, int max_iter, float tol,
-                              float lam_floor, const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream_) {
+                              float lam_floor, int n_converge, const int32_t* seg_off, const int64_t* a_off,
+                              msvit_stream_t stream_) {
   using namespace msvit;
   using namespace msvit::eig;
   if (!A || !deg || !V || !lam) return MSVIT_ERR_NULL;
   if (S < 0 || N <= 0 || k <= 0 || total_rows < 0 || max_iter <= 0 || !(tol > 0.f)) return MSVIT_ERR_SHAPE;
   if (block < k || block > MSVIT_MAX_EIG_BLOCK || (block & 3) != 0) return MSVIT_ERR_SHAPE;
+  if (n_converge < 0 || n_converge > k) return MSVIT_ERR_SHAPE;
   if (!seg_off && total_rows != static_cast<int64_t>(S) * N) return MSVIT_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return MSVIT_ERR_ALIGN;
   if (S == 0 || total_rows == 0) return MSVIT_OK;
@@ -1075,6 +1078,7 @@ extern "C" int msvit_ncut_eig(const float* A, const float* deg, float* V, float*
   P.A = A; P.deg = deg; P.V = V; P.lam = lam; P.iters = iters;
   P.seg_off = seg_off; P.a_off = a_off;
   P.S = S; P.N = N; P.k = k; P.m = block;
+  P.kconv = n_converge > 0 ? n_converge : k;
   P.max_iter = max_iter; P.rr_every = EIG_RR_EVERY; P.tol = tol; P.lam_floor = lam_floor;
   P.fast_iters = EIG_FAST_ITERS;
   if (block <= 16) return launch_threads<1>(P, stream);

@@ -30,7 +30,7 @@ _SIGNATURES = {
     "msvit_affinity_degree": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_f32,
                                        _c_f32, _c_ptr, _c_ptr, _c_ptr]),
     "msvit_ncut_eig": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int,
-                                _c_f32, _c_f32, _c_ptr, _c_ptr, _c_ptr]),
+                                _c_f32, _c_f32, _c_int, _c_ptr, _c_ptr, _c_ptr]),
     "msvit_kmeans": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int,
                               _c_int, _c_f32, _c_int, _c_ptr, _c_ptr]),
     "msvit_pool": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr]),

@@ -78,6 +78,8 @@ class ClusterPlan:
         self.thr = float(eigenvalue_threshold) if eigenvalue_threshold is not None else 0.0
         # eigenpairs below half the threshold are never clustered on: exempt them from the residual test
         self.lam_floor = 0.5 * self.thr if self.nk == 0 else 0.0
+        # with a fixed number of clusters K < k the k-means step reads V[:, :K] only: the other pairs need not converge
+        self.n_converge = min(self.nk, self.k) if self.nk > 0 else 0
         self.kmeans_iters, self.eig_iters, self.eig_tol = int(kmeans_iters), int(eig_iters), float(eig_tol)
         self.want_pool = bool(want_pool)
         self.Kp = int(pool_k) if pool_k is not None else self.P * (self.nk if self.nk > 0 else self.k)
@@ -145,8 +147,8 @@ class ClusterPlan:
                   "msvit_affinity_degree")
             mark(2)
             check(lib.msvit_ncut_eig(p(self.A), p(self.deg), p(self.V), p(self.lam), p(self.iters), rows, S, N, k,
-                                     self.block, self.eig_iters, self.eig_tol, self.lam_floor, p(self.seg_off),
-                                     p(self.a_off), st), "msvit_ncut_eig")
+                                     self.block, self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge,
+                                     p(self.seg_off), p(self.a_off), st), "msvit_ncut_eig")
             mark(3)
             check(lib.msvit_kmeans(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted), p(self.n_child),
                                    None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters, p(self.seg_off), st),
@@ -216,14 +218,14 @@ def affinity(x: torch.Tensor, mode: str = "rbf", gamma: float = 3.0, scale: Opti
 
 
 def ncut_eig(A: torch.Tensor, deg: torch.Tensor, k: int, *, max_iter: int = 60, tol: float = 2e-5, oversample: int = 8,
-             lam_floor: float = 0.0):
+             lam_floor: float = 0.0, n_converge: int = 0):
     """A [B, N, lda] (as returned by `affinity`), deg [B, N] -> (V [B, N, k], lam [B, k], iters [B])."""
     B, N, lda = A.shape
     if lda != ops.lda_of(N):
         raise ValueError("A must be [B, N, (N+3)&~3]")
     V, lam, iters = ops.ncut_eig(A.contiguous().view(-1), deg.contiguous().view(-1), B, N, int(k),
                                  default_block(int(k), oversample), int(max_iter), float(tol), float(lam_floor),
-                                 None, None)
+                                 int(n_converge), None, None)
     return V.view(B, N, k), lam, iters
 
 

@@ -71,7 +71,7 @@ def _(x, S, N, mode, gamma, scale, seg_off, a_off, a_numel, want_affinity):
 
 @torch.library.custom_op("msvit::ncut_eig", mutates_args=(), device_types="cuda")
 def ncut_eig(A: torch.Tensor, deg: torch.Tensor, S: int, N: int, k: int, block: int, max_iter: int, tol: float,
-             lam_floor: float, seg_off: Optional[torch.Tensor],
+             lam_floor: float, n_converge: int, seg_off: Optional[torch.Tensor],
              a_off: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """-> (V [rows, k], lam [S, k], iters [S] int32)."""
     _need_cuda(A, deg, seg_off, a_off)
@@ -81,13 +81,14 @@ def ncut_eig(A: torch.Tensor, deg: torch.Tensor, S: int, N: int, k: int, block: 
         lam = torch.empty(S, k, dtype=torch.float32, device=A.device)
         iters = torch.empty(S, dtype=torch.int32, device=A.device)
         code = _lib.load().msvit_ncut_eig(_ptr(A), _ptr(deg), _ptr(V), _ptr(lam), _ptr(iters), rows, S, N, k, block,
-                                          max_iter, tol, lam_floor, _ptr(seg_off), _ptr(a_off), _stream(A))
+                                          max_iter, tol, lam_floor, n_converge, _ptr(seg_off), _ptr(a_off),
+                                          _stream(A))
     _lib.check(code, "msvit_ncut_eig")
     return V, lam, iters
 
 
 @ncut_eig.register_fake
-def _(A, deg, S, N, k, block, max_iter, tol, lam_floor, seg_off, a_off):
+def _(A, deg, S, N, k, block, max_iter, tol, lam_floor, n_converge, seg_off, a_off):
     rows = deg.shape[0]
     return (A.new_empty(rows, k), A.new_empty(S, k), A.new_empty(S, dtype=torch.int32))
 

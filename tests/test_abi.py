@@ -47,8 +47,9 @@ def test_argument_checks_fire_before_any_cuda_call(lib):
     assert lib.msvit_affinity_degree(p16, 0, None, p16, 9, 1, 8, 8, 0, 3.0, 1.0, None, None, None) == -2  # rows != S*N
     assert lib.msvit_affinity_degree(p16, 1, None, p16, 8, 1, 8, 3, 0, 3.0, 1.0, None, None, None) == -3  # row stride
     assert lib.msvit_affinity_degree(p16 + 4, 0, None, p16, 8, 1, 8, 8, 0, 3.0, 1.0, None, None, None) == -3
-    assert lib.msvit_ncut_eig(p16, p16, p16, p16, None, 8, 1, 8, 4, 6, 10, 1e-5, 0.0, None, None, None) == -2  # block % 4
-    assert lib.msvit_ncut_eig(p16, p16, p16, p16, None, 8, 1, 8, 40, 40, 10, 1e-5, 0.0, None, None, None) == -2  # block > max
+    assert lib.msvit_ncut_eig(p16, p16, p16, p16, None, 8, 1, 8, 4, 6, 10, 1e-5, 0.0, 0, None, None, None) == -2  # block % 4
+    assert lib.msvit_ncut_eig(p16, p16, p16, p16, None, 8, 1, 8, 40, 40, 10, 1e-5, 0.0, 0, None, None, None) == -2  # block > max
+    assert lib.msvit_ncut_eig(p16, p16, p16, p16, None, 8, 1, 8, 4, 8, 10, 1e-5, 0.0, 5, None, None, None) == -2  # n_converge > k
     assert lib.msvit_kmeans(p16, None, None, None, p16, p16, None, 8, 1, 8, 4, 0, 0.1, 10, None, None) == -1  # lam needed
     assert lib.msvit_pool(p16, 0, None, p16, p16, 1, 8, 8, 2, None) == -1
     assert lib.msvit_pool(p16, 0, p16, p16, p16, 1, 8, 8, 0, None) == -2

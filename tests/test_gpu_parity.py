@@ -307,3 +307,20 @@ def test_attention_mask_matches_reference_restatement(shape):
     assert torch.equal(got.cpu(), ref)
     C = int(lab.max()) + 1
     assert torch.equal(msvit.attention_mask(lab.to(DEV), max_n_clusters=C).cpu(), ref)   # no host read of the labels
+
+
+def test_ncut_eig_partial_convergence_request():
+    # fixed K < ncut_dim: only the K pairs the k-means step reads must meet the tolerance (modeling_spectral.py:90);
+    # they match the exact decomposition, and the solver stops early instead of chasing the noise-bulk pairs
+    N, D, Kp, k = 256, 64, 3, 8
+    B = 2
+    x, _ = planted_tokens(B, N, D, Kp)
+    A = torch.stack([O.affinity(x[b], "rbf", 3.0, default_scale(D)) for b in range(B)])
+    deg = A.sum(-1)
+    V_all, lam_all, it_all = F.ncut_eig(A.to(DEV), deg.to(DEV), k)
+    V, lam, it = F.ncut_eig(A.to(DEV), deg.to(DEV), k, n_converge=Kp)
+    assert int(it.max()) <= int(it_all.max())
+    for b in range(B):
+        Vref, lref, _ = O.ncut_eig(A[b].double(), k + 4)
+        np.testing.assert_allclose(lam[b, :Kp].cpu().numpy(), lref[:Kp].numpy(), rtol=RTOL, atol=1e-6)
+        check_eigvecs(V[b], lref.tolist(), Vref, Kp)

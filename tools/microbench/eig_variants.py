@@ -66,14 +66,14 @@ def run(argv):
         lib = ctypes.CDLL(path)
         fn = lib.msvit_ncut_eig
         fn.restype = ctypes.c_int
-        fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [ctypes.c_float] * 2 + [ctypes.c_void_p] * 3
+        fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int64] + [ctypes.c_int] * 5 + [ctypes.c_float] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 3
         V = torch.empty(B * N, k, device=dev)
         lam = torch.empty(B, k, device=dev)
         iters = torch.empty(B, dtype=torch.int32, device=dev)
 
         def call():
             rc = fn(A.data_ptr(), deg.data_ptr(), V.data_ptr(), lam.data_ptr(), iters.data_ptr(), B * N, B, N, k, block, 60,
-                    2e-5, 0.0, None, None, st)
+                    2e-5, 0.0, 0, None, None, st)
             assert rc == 0, rc
         for _ in range(3):
             call()
