@@ -6,8 +6,10 @@
 // :130-133 and :277-278.  Deterministic restatement: farthest-point seeding, lowest-index tie breaks,
 // empty cluster keeps its centre, first-occurrence relabelling (oracle/ncut_oracle.py:kmeans).
 //
-// Distance + argmin run in one pass per point; the centre update is a segmented, atomic-free sum in a
-// fixed order (thread (c, d) adds the members of cluster c in ascending token order).
+// The segment's embedding is staged once into shared memory (transposed: coordinate j of all points is contiguous,
+// so a warp reads it without bank conflicts).  Distance + argmin run in one pass per point; the centre update is a
+// segmented, atomic-free sum in a fixed order (thread (c, d, h) adds the members of cluster c in ascending token
+// order over half h of the tokens, the halves are combined in a fixed order).
 #include "common.cuh"
 
 namespace msvit {
@@ -51,10 +53,11 @@ __device__ __forceinline__ int block_argmax(float v, int idx, float* sval, int* 
   return r;
 }
 
-__device__ __forceinline__ float sqdist(const float* __restrict__ p, const float* __restrict__ c, int K) {
+// squared distance of point i (column i of the transposed embedding, row stride ldp) to centre c
+__device__ __forceinline__ float sqdist(const float* __restrict__ pt, int ldp, int i, const float* __restrict__ c, int K) {
   float d = 0.f;
   for (int j = 0; j < K; ++j) {
-    const float t = p[j] - c[j];
+    const float t = pt[j * ldp + i] - c[j];
     d = fmaf(t, t, d);
   }
   return d;
@@ -66,6 +69,10 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
   float* mind = cen + kMaxK * (kMaxK + 1);             // [N]
   int* lab = reinterpret_cast<int*>(mind + P.N);       // [N]
   int* map = lab + P.N;                                // [kMaxK]
+  float* part = reinterpret_cast<float*>(map + kMaxK); // [2][kMaxK * kMaxK] partial centre sums
+  int* pcnt = reinterpret_cast<int*>(part + 2 * kMaxK * kMaxK);  // [2][kMaxK] partial counts
+  float* pts = reinterpret_cast<float*>(pcnt + 2 * kMaxK);       // [Kcap][ldp] transposed embedding
+  const int ldp = P.N | 1;                             // odd row stride
   __shared__ float sval[kThreads / 32];
   __shared__ int sidx[kThreads / 32];
   __shared__ int s_changed;
@@ -88,6 +95,13 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
       K = K < 1 ? 1 : K;
     }
     K = min(K, min(n, min(P.ldv, kMaxK)));
+    // stage the K leading coordinates of the segment's points (coalesced global reads, transposed writes)
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * P.ldv; e += kThreads) {
+      const int i = e / P.ldv, j = e - i * P.ldv;
+      if (j < K) pts[j * ldp + i] = Pt[e];
+    }
+    __syncthreads();
 
     // ---- seeding
     if (P.init) {
@@ -106,19 +120,18 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
         first = block_argmax(bv, bi, sval, sidx);
         if (first < 0 || first >= n) first = 0;
       }
-      for (int j = threadIdx.x; j < K; j += kThreads) cen[j] = Pt[static_cast<long long>(first) * P.ldv + j];
+      for (int j = threadIdx.x; j < K; j += kThreads) cen[j] = pts[j * ldp + first];
       __syncthreads();
-      for (int i = threadIdx.x; i < n; i += kThreads) mind[i] = sqdist(Pt + static_cast<long long>(i) * P.ldv, cen, K);
+      for (int i = threadIdx.x; i < n; i += kThreads) mind[i] = sqdist(pts, ldp, i, cen, K);
       for (int c = 1; c < K; ++c) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         for (int i = threadIdx.x; i < n; i += kThreads)
           if (mind[i] > bv) { bv = mind[i]; bi = i; }
         const int nxt = block_argmax(bv, bi, sval, sidx);
-        for (int j = threadIdx.x; j < K; j += kThreads) cen[c * LDC + j] = Pt[static_cast<long long>(nxt) * P.ldv + j];
+        for (int j = threadIdx.x; j < K; j += kThreads) cen[c * LDC + j] = pts[j * ldp + nxt];
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kThreads)
-          mind[i] = fminf(mind[i], sqdist(Pt + static_cast<long long>(i) * P.ldv, cen + c * LDC, K));
+        for (int i = threadIdx.x; i < n; i += kThreads) mind[i] = fminf(mind[i], sqdist(pts, ldp, i, cen + c * LDC, K));
       }
     }
     for (int i = threadIdx.x; i < n; i += kThreads) lab[i] = -1;
@@ -130,11 +143,10 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
       __syncthreads();
       int changed = 0;
       for (int i = threadIdx.x; i < n; i += kThreads) {
-        const float* p = Pt + static_cast<long long>(i) * P.ldv;
         float bd = INFINITY;
         int bc = 0;
         for (int c = 0; c < K; ++c) {
-          const float d = sqdist(p, cen + c * LDC, K);
+          const float d = sqdist(pts, ldp, i, cen + c * LDC, K);
           if (d < bd) { bd = d; bc = c; }
         }
         if (lab[i] != bc) { lab[i] = bc; changed = 1; }
@@ -142,13 +154,25 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
       if (changed) s_changed = 1;
       __syncthreads();
       if (!s_changed) break;
-      for (int e = threadIdx.x; e < K * K; e += kThreads) {
-        const int c = e / K, d = e % K;
+      // partial sums over the two halves of the tokens (ascending order inside a half), then a fixed-order combine
+      const int nh = (n + 1) >> 1;
+      for (int e = threadIdx.x; e < 2 * K * K; e += kThreads) {
+        const int h = e / (K * K), r = e - h * K * K;
+        const int c = r / K, d = r - c * K;
+        const int i0 = h * nh, i1 = min(n, i0 + nh);
+        const float* pd = pts + d * ldp;
         float sum = 0.f;
         int cnt = 0;
-        for (int i = 0; i < n; ++i)
-          if (lab[i] == c) { sum += Pt[static_cast<long long>(i) * P.ldv + d]; ++cnt; }
-        if (cnt > 0) cen[c * LDC + d] = sum / static_cast<float>(cnt);
+        for (int i = i0; i < i1; ++i)
+          if (lab[i] == c) { sum += pd[i]; ++cnt; }
+        part[h * kMaxK * kMaxK + r] = sum;
+        if (d == 0) pcnt[h * kMaxK + c] = cnt;
+      }
+      __syncthreads();
+      for (int r = threadIdx.x; r < K * K; r += kThreads) {
+        const int c = r / K, d = r - c * K;
+        const int cnt = pcnt[c] + pcnt[kMaxK + c];
+        if (cnt > 0) cen[c * LDC + d] = (part[r] + part[kMaxK * kMaxK + r]) / static_cast<float>(cnt);
       }
       __syncthreads();
     }
@@ -196,7 +220,9 @@ extern "C" int msvit_kmeans(const float* V, const float* lam, const float* weigh
   P.centres = centres; P.seg_off = seg_off;
   P.S = S; P.N = N; P.ldv = ldv; P.n_clusters = n_clusters; P.Kmax = n_clusters > 0 ? n_clusters : ldv;
   P.max_iter = max_iter; P.thr = eig_threshold;
-  const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N) + sizeof(int) * (N + kMaxK);
+  const int kcap = P.Kmax < kMaxK ? P.Kmax : kMaxK;   // coordinates staged per point
+  const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N + 2 * kMaxK * kMaxK + static_cast<size_t>(kcap) * (N | 1)) +
+                      sizeof(int) * (N + kMaxK + 2 * kMaxK);
   if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_status(e);
