@@ -46,10 +46,16 @@
 #define EIG_MINB 4
 #endif
 #ifndef EIG_RR_EVERY   // scheduled whole-block Rayleigh-Ritz period
-#define EIG_RR_EVERY 3
+#define EIG_RR_EVERY 4
 #endif
 #ifndef EIG_SWEEPS     // Jacobi sweeps of a scheduled (not final) Rayleigh-Ritz step
 #define EIG_SWEEPS 2
+#endif
+// Cholesky QR loses orthogonality like eps / (smallest scaled pivot of the Gram matrix); it is repeated below this
+// pivot.  Early iterates (far from the Ritz basis) are ill conditioned but only need a well-conditioned basis, not an
+// orthonormal one: 1e-3 keeps |U^T D U - I| <~ 1e-4 there, and near convergence Y is almost D-orthogonal (pivot ~ 1).
+#ifndef EIG_REORTH
+#define EIG_REORTH 1e-3f
 #endif
 #ifndef EIG_FAST_ITERS // leading products done in a single TF32 pass
 #define EIG_FAST_ITERS 2
@@ -60,7 +66,8 @@ namespace eig {
 
 #ifdef EIG_PROFILE
 // Development instrumentation: cycles thread 0 of every CTA spends in each phase (tools/microbench/eig_variants.py).
-enum { PH_INIT, PH_MATVEC, PH_GRAMS, PH_TRIGGER, PH_JACOBI, PH_ROTATE, PH_CHOL, PH_ORTH, PH_OUTPUT, PH_COUNT };
+enum { PH_INIT, PH_MATVEC, PH_GRAMS, PH_TRIGGER, PH_JACOBI, PH_ROTATE, PH_CHOL, PH_ORTH, PH_OUTPUT, PH_FACT, PH_INV,
+       PH_COUNT };
 __device__ unsigned long long g_phase_cycles[PH_COUNT];
 #define PHASE_BEGIN() long long ph_t0 = clock64()
 #define PHASE_END(ph)                                                                          \
@@ -118,7 +125,7 @@ __host__ __device__ inline Layout make_layout(int N, int m, int MT, int nwarps) 
   L.Hs = o;      o += mm;
   L.Ss = o;      o += mm;
   L.Ws = o;      o += mm;
-  L.pinv = o;    o += MSVIT_MAX_EIG_BLOCK;
+  L.pinv = o;    o += MSVIT_MAX_EIG_BLOCK + 128;          // reciprocal pivots, then 2 x 64 floats of Cholesky scratch
   L.misc = o;    o += 8 + 3 * MSVIT_MAX_EIG_BLOCK;
   L.colred = o;  o += nwarps * MSVIT_MAX_EIG_BLOCK;
   L.rot = o;     o += 4 * (MSVIT_MAX_EIG_BLOCK / 2);
@@ -603,47 +610,53 @@ __device__ __forceinline__ float cholesky_inverse(float* __restrict__ G, int m, 
   const int ld = m + 1;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
+    PHASE_BEGIN();
     {
+      // Right-looking factorisation.  Lane i keeps the not-yet-eliminated part of row i in registers, shifted so that
+      // g[0] is the current column.  One step: every lane publishes g[0] (= column j of the Schur complement) in
+      // shared memory, reads the pivot and the 15 entries below it as broadcast loads (a chain of warp shuffles
+      // each feeding one multiply-add costs ~60 cycles per pair on the in-order pipe), scales, and applies the
+      // rank-1 update fused with the shift.  L[i][j] = s_ij / sqrt(s_jj);  s'_ik = s_ik - s_ij s_kj / s_jj.
+      float* colbuf = pinv + MSVIT_MAX_EIG_BLOCK;  // 2 x 32 floats of scratch (reserved behind pinv, see Layout)
       const int row = lane < me ? lane : 0;
       float g[MB];
 #pragma unroll
-      for (int c = 0; c < MB; ++c) g[c] = (c < me) ? G[row * ld + c] : 0.f;
+      for (int c = 0; c < MB; ++c) g[c] = (c < me && lane < me) ? G[row * ld + c] : 0.f;
+      const float dorig = (lane < me) ? G[row * ld + row] : 0.f;
       float minpiv = 1.0f;
+#pragma unroll 1
+      for (int j = 0; j < me; ++j) {
+        float* col = colbuf + (j & 1) * 64;
+        col[lane] = g[0];
+        col[32 + lane] = 0.f;  // reads past lane 31 (j + c > 31) see zeros
+        __syncwarp();
+        const float piv = col[j];
+        const float gjj = __shfl_sync(0xffffffffu, dorig, j);
+        float below[MB];
 #pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        if (j < me) {  // warp-uniform
-          // s_i = G[i][j] - sum_{c<j} L[i][c] L[j][c]; lane j's value is the pivot
-          float s0 = g[j], s1 = 0.f;
-#pragma unroll
-          for (int c = 0; c + 1 < j; c += 2) {
-            s0 = fmaf(-g[c], __shfl_sync(0xffffffffu, g[c], j), s0);
-            s1 = fmaf(-g[c + 1], __shfl_sync(0xffffffffu, g[c + 1], j), s1);
-          }
-          if (j & 1) s0 = fmaf(-g[j - 1], __shfl_sync(0xffffffffu, g[j - 1], j), s0);
-          const float s = s0 + s1;
-          const float piv = __shfl_sync(0xffffffffu, s, j);
-          const float gjj = __shfl_sync(0xffffffffu, g[j], j);
-          const float rel = gjj > 0.f ? __fdividef(piv, gjj) : 0.f;
-          const bool ok = rel > 1e-6f && piv > 0.f;
-          minpiv = fminf(minpiv, ok ? rel : 1.0f);
-          float inv = 0.f, ljj = 0.f;
-          if (ok) {
-            inv = rsqrtf(piv);
-            inv = inv * (1.5f - 0.5f * piv * inv * inv);  // one Newton step: fp32-accurate 1/sqrt
-            ljj = piv * inv;
-          }
-          g[j] = lane == j ? ljj : (lane > j ? s * inv : 0.f);
-          if (lane == j) pinv[j] = inv;
+        for (int c = 1; c < MB; ++c) below[c] = col[j + c];
+        const float rel = gjj > 0.f ? __fdividef(piv, gjj) : 0.f;
+        const bool ok = rel > 1e-6f && piv > 0.f;
+        minpiv = fminf(minpiv, ok ? rel : 1.0f);
+        float inv = 0.f, ljj = 0.f;
+        if (ok) {
+          inv = rsqrtf(piv);
+          inv = inv * (1.5f - 0.5f * piv * inv * inv);  // one Newton step: fp32-accurate 1/sqrt
+          ljj = piv * inv;
         }
-      }
-      if (lane < me) {
+        const bool mine = lane > j && lane < me;
+        const float l = lane == j ? ljj : (mine ? g[0] * inv : 0.f);  // L[lane][j]
+        if (lane >= j && lane < me) G[lane * ld + j] = l;
+        if (lane == j) pinv[j] = inv;
+        const float f = mine ? g[0] * inv * inv : 0.f;  // s_ij / s_jj
 #pragma unroll
-        for (int c = 0; c < MB; ++c)
-          if (c <= lane && c < me) G[lane * ld + c] = g[c];
+        for (int c = 1; c < MB; ++c) g[c - 1] = fmaf(-f, below[c], g[c]);
+        g[MB - 1] = 0.f;
       }
       if (lane == 0) misc[0] = minpiv;
     }
     __syncwarp();
+    PHASE_END(PH_FACT);
     {
       // w_ij = pinv_i * (delta_ij - sum_{c<i} L[i][c] w_cj)
       float w[MB];
@@ -668,6 +681,7 @@ __device__ __forceinline__ float cholesky_inverse(float* __restrict__ G, int m, 
           if (i < m) W[i * ld + lane] = (i < me && lane <= i) ? w[i] : 0.f;
       }
     }
+    PHASE_END(PH_INV);
   }
   __syncthreads();
   return misc[0];
@@ -972,7 +986,7 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
       PHASE_END(PH_CHOL);
       orthonormalise<MT, NWARPS>(Ws, m, Yt, Ut, Uf, npad, ldt, rows);
       PHASE_END(PH_ORTH);
-      if (piv < 0.05f) {
+      if (piv < EIG_REORTH) {
         weighted_grams<NWARPS>(Ut, Ut, dg, n, m, ldt, rows, Gs, Hs, false);
         cholesky_inverse<MB>(Gs, m, me, pinv, Ws, misc);
         orthonormalise<MT, NWARPS>(Ws, m, Ut, Ut, Uf, npad, ldt, rows);

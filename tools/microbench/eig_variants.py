@@ -73,7 +73,7 @@ def run(argv):
 
         def call():
             rc = fn(A.data_ptr(), deg.data_ptr(), V.data_ptr(), lam.data_ptr(), iters.data_ptr(), B * N, B, N, k, block, 60,
-                    2e-5, 0.0, 0, None, None, st)
+                    float(os.environ.get("EIG_TOL", "2e-5")), 0.0, 0, None, None, st)
             assert rc == 0, rc
         for _ in range(3):
             call()
@@ -92,13 +92,13 @@ def run(argv):
             msg += f"  dlam {float((lam - ref[1]).abs().max()):.2e}  dV {float((V - ref[0]).abs().max()):.2e}"
         print(msg, flush=True)
         if hasattr(lib, "msvit_eig_profile"):
-            buf = (ctypes.c_ulonglong * 9)()
+            buf = (ctypes.c_ulonglong * 11)()
             lib.msvit_eig_profile(buf, 1)
             call()
             torch.cuda.synchronize()
             lib.msvit_eig_profile(buf, 1)
-            names = ["init", "matvec", "grams", "trigger", "jacobi", "rotate", "chol", "orth", "output"]
-            tot = sum(buf)
+            names = ["init", "matvec", "grams", "trigger", "jacobi", "rotate", "chol", "orth", "output", "(fact", "inv)"]
+            tot = sum(buf[:9])
             print("    cycles/segment: " + "  ".join(f"{n} {buf[i] / B:.0f}" for i, n in enumerate(names)) + f"  total {tot / B:.0f}",
                   flush=True)
 
