@@ -92,3 +92,79 @@ extern "C" int msvit_attention_mask(const int64_t* cluster_indices, uint8_t* mas
   mask::attention_mask_kernel<<<dim3(gx, B), 256, static_cast<size_t>(N) * sizeof(int), stream>>>(cluster_indices, mask, N, C);
   return cuda_status(cudaGetLastError());
 }
+
+// ----------------------------------------------------------------------------- cluster-compressed attention
+// Transmitter statistics of compress_tokens_with_cluster_indices
+// (model/multistate_encoder/modeling_msvitencoder.py:182-186):
+//     out[b, h, q, c] = sum_{k : cluster(b, k) = c} attn[b, h, q, k]
+// (the reference multiplies by a one-hot [N, C] mask through a 5-D broadcast and sums).  One warp per attention row,
+// 128-bit loads along k, C predicated accumulators per lane, fixed-order warp reduction: the attention tensor is
+// read exactly once (HBM-read bound, B*H*N*N*4 bytes).  The receiver statistics of the same function (:187-190,
+// mean over the QUERY tokens of a cluster) are msvit_pool applied to the [B*H, N, N] view.
+namespace msvit {
+namespace mask {
+
+template <int CMAX>
+__global__ void __launch_bounds__(256) key_sums_kernel(const float* __restrict__ attn,
+                                                       const int64_t* __restrict__ cluster_indices,
+                                                       float* __restrict__ out, int H, int N, int C) {
+  extern __shared__ int lab[];  // [N rounded up to 4] labels of this image (pad = -1)
+  const int bh = blockIdx.y, b = bh / H;
+  const int N4 = (N + 3) & ~3;
+  for (int i = threadIdx.x; i < N4; i += blockDim.x)
+    lab[i] = i < N ? static_cast<int>(cluster_indices[static_cast<size_t>(b) * N + i]) : -1;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const bool vec = (N & 3) == 0;
+  for (int q = blockIdx.x * nwarps + warp; q < N; q += gridDim.x * nwarps) {
+    const float* row = attn + (static_cast<size_t>(bh) * N + q) * N;
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+    if (vec) {
+      for (int k = 4 * lane; k < N; k += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(row + k);
+        const int4 l = *reinterpret_cast<const int4*>(lab + k);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          acc[c] += (l.x == c ? a.x : 0.f) + (l.y == c ? a.y : 0.f) + (l.z == c ? a.z : 0.f) + (l.w == c ? a.w : 0.f);
+      }
+    } else {
+      for (int k = lane; k < N; k += 32) {
+        const float a = row[k];
+        const int l = lab[k];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) acc[c] += l == c ? a : 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    float* o = out + (static_cast<size_t>(bh) * N + q) * C;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (lane == (c & 31) && c < C) o[c] = acc[c];
+  }
+}
+
+}  // namespace mask
+}  // namespace msvit
+
+extern "C" int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_indices, float* out, int B, int H, int N,
+                                      int C, msvit_stream_t stream_) {
+  using namespace msvit;
+  if (!attn || !cluster_indices || !out) return MSVIT_ERR_NULL;
+  if (B < 0 || H <= 0 || N <= 0 || C <= 0 || C > 32 || N > 8192 || static_cast<long long>(B) * H > 65535) return MSVIT_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(attn) & 15) != 0) return MSVIT_ERR_ALIGN;
+  if (B == 0) return MSVIT_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int gx = (N + 63) / 64;  // 8 warps x 8 rows per CTA
+  const dim3 grid(gx, B * H);
+  const size_t smem = static_cast<size_t>((N + 3) & ~3) * sizeof(int);
+  if (C <= 8) mask::key_sums_kernel<8><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
+  else if (C <= 16) mask::key_sums_kernel<16><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
+  else mask::key_sums_kernel<32><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
+  return cuda_status(cudaGetLastError());
+}

@@ -9,8 +9,8 @@ from . import _lib
 from .clustering import (CLUSTERING_CLASSES, ClusteringConfig, ClusteringModule, SpectralClustering,
                          SpectralClusteringConfig)
 from .global_kmeans import GlobalKMeansPlan, GlobalKMeansResult, global_kmeans
-from .functional import ClusterOutput, ClusterPlan, HostClusterer, HostResult, affinity, attention_mask, cluster_tokens, kmeans, ncut_eig, pool
+from .functional import ClusterOutput, ClusterPlan, HostClusterer, HostResult, affinity, attention_mask, cluster_attention_stats, cluster_tokens, kmeans, ncut_eig, pool
 
 __all__ = ["CLUSTERING_CLASSES", "ClusteringConfig", "ClusteringModule", "SpectralClustering",
-           "SpectralClusteringConfig", "ClusterOutput", "ClusterPlan", "HostClusterer", "HostResult", "affinity", "attention_mask", "cluster_tokens", "kmeans", "ncut_eig", "pool",
+           "SpectralClusteringConfig", "ClusterOutput", "ClusterPlan", "HostClusterer", "HostResult", "affinity", "attention_mask", "cluster_attention_stats", "cluster_tokens", "kmeans", "ncut_eig", "pool",
            "GlobalKMeansPlan", "GlobalKMeansResult", "global_kmeans", "_lib"]

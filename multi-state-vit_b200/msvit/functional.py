@@ -270,6 +270,33 @@ def attention_mask(cluster_indices: torch.Tensor, max_n_clusters: Optional[int] 
     return mask.view(torch.bool)
 
 
+def cluster_attention_stats(attention_probs: torch.Tensor, cluster_indices: torch.Tensor, n_clusters: int):
+    """Cluster-compressed attention statistics of compress_tokens_with_cluster_indices (msvitencoder.py:182-190):
+
+        transmitter [B, H, N, C] = sum of attention_probs[b, h, q, :] over the KEYS of each cluster
+        receiver    [B, H, C, N] = mean of attention_probs[b, h, :, k] over the QUERIES of each cluster (empty -> 0)
+
+    attention_probs [B, H, N, N] fp32, cluster_indices [B, N] int64; the reference materialises a 5-D broadcast."""
+    if attention_probs.dim() != 4 or attention_probs.shape[-1] != attention_probs.shape[-2]:
+        raise ValueError("attention_probs must be [batch, heads, tokens, tokens]")
+    if not attention_probs.is_cuda:
+        raise RuntimeError("msvit.cluster_attention_stats runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if attention_probs.dtype != torch.float32:
+        raise TypeError("attention_probs must be float32")
+    B, H, N, _ = attention_probs.shape
+    C = int(n_clusters)
+    a = attention_probs.contiguous()
+    lab = cluster_indices.contiguous()
+    with torch.cuda.device(a.device):
+        tr = torch.empty(B, H, N, C, dtype=torch.float32, device=a.device)
+        st = torch.cuda.current_stream(a.device).cuda_stream
+        _lib.check(_lib.load().msvit_cluster_key_sums(ops._ptr(a), ops._ptr(lab), ops._ptr(tr), B, H, N, C, st),
+                   "msvit_cluster_key_sums")
+        lab_h = lab[:, None, :].expand(B, H, N).reshape(B * H, N).contiguous()
+        rc, _ = ops.pool(a.view(B * H, N, N), lab_h, C)
+    return tr, rc.view(B, H, C, N)
+
+
 @dataclass
 class HostResult:
     labels: torch.Tensor   # [B, N] int64, pinned host memory

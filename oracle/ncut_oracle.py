@@ -281,6 +281,18 @@ def attention_mask(cluster_indices: torch.Tensor) -> torch.Tensor:
     return mask[:, None]
 
 
+def cluster_attention_stats(attention_probs: torch.Tensor, cluster_indices: torch.Tensor, n_clusters: int):
+    """Restates the transmitter / receiver statistics of compress_tokens_with_cluster_indices
+    (model/multistate_encoder/modeling_msvitencoder.py:182-190): one-hot masks [B, N, C]; transmitter = attention
+    summed over the keys of each cluster [B, H, N, C]; receiver = attention averaged over the queries of each
+    cluster [B, H, C, N] (an empty cluster gives 0 here, 0/0 in the reference)."""
+    masks = (cluster_indices[..., None] == torch.arange(n_clusters)).to(attention_probs.dtype)     # [B, N, C]
+    transmitter = torch.einsum("bhqk,bkc->bhqc", attention_probs, masks)
+    counts = masks.sum(1)                                                                          # [B, C]
+    receiver = torch.einsum("bhqk,bqc->bhck", attention_probs, masks) / counts.clamp(min=1)[:, None, :, None]
+    return transmitter, receiver
+
+
 # --------------------------------------------------------------------------- helpers for tests
 def round_to_bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(x.dtype)

@@ -324,3 +324,18 @@ def test_ncut_eig_partial_convergence_request():
         Vref, lref, _ = O.ncut_eig(A[b].double(), k + 4)
         np.testing.assert_allclose(lam[b, :Kp].cpu().numpy(), lref[:Kp].numpy(), rtol=RTOL, atol=1e-6)
         check_eigvecs(V[b], lref.tolist(), Vref, Kp)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 196, 8), (1, 2, 50, 5), (2, 1, 33, 12), (1, 4, 256, 20)])
+def test_cluster_attention_stats_match_reference_restatement(shape):
+    # compress_tokens_with_cluster_indices (msvitencoder.py:182-190): transmitter sums and receiver means
+    B, H, N, C = shape
+    g = torch.Generator().manual_seed(N + C)
+    attn = torch.softmax(torch.randn(B, H, N, N, generator=g), dim=-1)
+    lab = torch.randint(0, C, (B, N), generator=g)
+    lab[0, lab[0] == C - 1] = 0          # an empty cluster
+    tr_ref, rc_ref = O.cluster_attention_stats(attn.double(), lab, C)
+    tr, rc = msvit.cluster_attention_stats(attn.to(DEV), lab.to(DEV), C)
+    torch.testing.assert_close(tr.cpu().double(), tr_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rc.cpu().double(), rc_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(tr.sum(-1).cpu(), torch.ones(B, H, N), rtol=1e-5, atol=1e-5)   # rows of a softmax
