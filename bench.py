@@ -323,6 +323,13 @@ def run_ours(args):
         roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["_source"]}
     roof["share_of_step"] = round(stages[dominant]["ms"] / sum(s["ms"] for s in stages.values()), 3)
+    if dominant == "eig":
+        # the eigensolver is bound by per-segment dependency latency, not by a pipe (profiles/r1c_summary.md): its
+        # HBM figure is the compulsory traffic (affinity once); its tensor-core products are reported next to it
+        m = plan.block
+        fl = 2.0 * B * N * N * m * eig_iters["mean"]
+        roof["note"] = "latency-bound (4 CTAs/SM, two waves); hbm = compulsory bytes (affinity read once)"
+        roof["products_tflops"] = round(fl / stages["eig"]["ms"] / 1e9, 2)
 
     cpu_rate, cores, cpu_s, cpu_n = cpu_oracle_rate(N, D, K, k, args.cpu_images)
 

@@ -39,6 +39,15 @@ for what in "$@"; do
           bench.py --gpus 2 > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err
       echo "c2x2 rc=$?"; cat gpurun_out/bench_x2.json; tail -3 gpurun_out/bench_x2.err
       ;;
+    scale:*)
+      NG="${what#scale:}"
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 \
+          bench.py --gpus $NG --steps 10 --cpu-images 64 > gpurun_out/bench_x$NG.json 2> gpurun_out/bench_x$NG.err
+      echo "c2 x$NG rc=$?"; grep '^{' gpurun_out/bench_x$NG.json | cut -c1-400; tail -2 gpurun_out/bench_x$NG.err
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29514 \
+          bench.py --gpus $NG --config C5 --steps 10 > gpurun_out/bench_c5x$NG.json 2> gpurun_out/bench_c5x$NG.err
+      echo "c5 x$NG rc=$?"; grep '^{' gpurun_out/bench_c5x$NG.json | cut -c1-1300; tail -2 gpurun_out/bench_c5x$NG.err
+      ;;
     launches)
       CMD="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --cpu-images 8"
       timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
