@@ -39,8 +39,11 @@
 #ifndef EIG_T          // 8-row tiles of A per matvec pass when m <= 16
 #define EIG_T 4
 #endif
-#ifndef EIG_PF         // 16-column blocks of A in flight per lane in the matvec
-#define EIG_PF 4
+#ifndef EIG_PF         // 16-column blocks of A loaded together per lane in the matvec (one L2 round trip per batch)
+#define EIG_PF 3
+#endif
+#ifndef EIG_BATCH      // 1: load EIG_PF blocks together, then multiply them (see matvec_pass); 0: rolling window
+#define EIG_BATCH 1
 #endif
 #ifndef EIG_MINB       // CTAs per SM the register budget is sized for, at 128 threads
 #define EIG_MINB 4
@@ -237,6 +240,24 @@ __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int ld
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[q][mt][e] = 0.f;
   }
+#if EIG_BATCH
+  // batch mode: all global loads of a warp complete on one hardware scoreboard, so a rolling prefetch window
+  // degenerates to one exposed L2 round trip per block.  Instead PF blocks are loaded together, then multiplied:
+  // one round trip per PF blocks.
+  for (int kb0 = 0; kb0 < KB; kb0 += PF) {
+#pragma unroll
+    for (int s = 0; s < PF; ++s) {
+      const int kb = kb0 + s;
+      const bool ok = kb + 1 < KB || (kb < KB && last_ok);
+      const float* ak = Ag + 16 * kb;
+#pragma unroll
+      for (int q = 0; q < TC; ++q) x[s][q] = ok ? __ldcg(reinterpret_cast<const float4*>(ak + off[q])) : zero4;
+    }
+#pragma unroll
+    for (int s = 0; s < PF; ++s)
+      if (kb0 + s < KB) matvec_block<MT, TC, FULL>(acc, x[s], uf, kb0 + s);
+  }
+#else
 #pragma unroll
   for (int s = 0; s < PF; ++s) {
     const bool ok = s + 1 < KB || (s < KB && last_ok);
@@ -260,6 +281,7 @@ __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int ld
       }
     }
   }
+#endif
 #pragma unroll
   for (int q = 0; q < TC; ++q) {
     const int i = 8 * (tile0 + q) + 2 * t;
