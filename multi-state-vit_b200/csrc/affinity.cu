@@ -59,6 +59,10 @@ struct Shared {
   float rowq[kTile];
   float colq[kTile];
   float degp[2][kTile];
+  // per-warp transposition tile of the epilogue: 32 accumulator rows x 16 columns (row stride 20 floats), so that
+  // the affinity is stored as 64-byte row segments (8 rows per store instruction) instead of one 16-byte piece
+  // per lane in 32 different rows
+  alignas(16) float stage[kEpiThreads / 32][32 * 20];
 };
 
 // Sum of squares of one 128-byte row of a k-slice as the tensor core sees it.
@@ -293,7 +297,8 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
             tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 256 + c * 16, v);
             const float rq = half ? rq1 : rq0;
             const bool valid = half ? v1 : v0;
-            float* __restrict__ arow = half ? arow1 : arow0;
+            float* __restrict__ abase = half ? arow1 : arow0;  // this lane's own row (used for the row offset only)
+            float* st = sh.stage[e];
             float rs = 0.f;
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
@@ -305,10 +310,24 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
                 a[i] = col < cols_here ? fast_exp2(l2) : 0.f;
                 rs += a[i];
               }
-              if (valid && arow && c * 16 + i4 * 4 < lda_here)
-                *reinterpret_cast<float4*>(arow + c * 16 + i4 * 4) = make_float4(a[0], a[1], a[2], a[3]);
+              if (abase) *reinterpret_cast<float4*>(st + lane * 20 + i4 * 4) = make_float4(a[0], a[1], a[2], a[3]);
             }
             if (half) rowsum1 += rs; else rowsum0 += rs;
+            if (abase) {
+              __syncwarp();
+              // lane l stores columns 4 (l % 4) .. +3 of the rows l / 4 + 8 pass of this 32-row group
+              const int cc = c * 16 + (lane & 3) * 4;
+              const int rbase = half * 128 + q * 32;  // first tile row of the group
+              float* __restrict__ g0 = P.A + g.a0 + static_cast<long long>(p * kTile + rbase) * g.lda + nt * kTile + cc;
+#pragma unroll
+              for (int pass = 0; pass < 4; ++pass) {
+                const int rr = (lane >> 2) + 8 * pass;
+                if (rbase + rr < rows_here && cc < lda_here)
+                  *reinterpret_cast<float4*>(g0 + static_cast<long long>(rr) * g.lda) =
+                      *reinterpret_cast<const float4*>(st + rr * 20 + (lane & 3) * 4);
+              }
+              __syncwarp();
+            }
           }
         }
         tc_fence_before();
