@@ -339,3 +339,16 @@ def test_cluster_attention_stats_match_reference_restatement(shape):
     torch.testing.assert_close(tr.cpu().double(), tr_ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(rc.cpu().double(), rc_ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(tr.sum(-1).cpu(), torch.ones(B, H, N), rtol=1e-5, atol=1e-5)   # rows of a softmax
+
+
+def test_cluster_tokens_cosine_distance_matches_oracle():
+    # model/clustering/modeling_spectral.py:62-69: the cosine variant of the NCUT affinity, whole path, bf16 tokens
+    B, N, D, K = 4, 196, 768, 8
+    x, planted = planted_tokens(B, N, D, K)
+    out = msvit.cluster_tokens(x.bfloat16().to(DEV), ncut_dim=K, n_clusters=K, mode="cosine", gamma=0.5)
+    xq = O.round_to_bf16(x)
+    child, _, eigvals, _ = O.cluster_tokens(xq.double(), None, ncut_dim=K, n_clusters=K, mode="cosine", gamma=0.5)
+    assert torch.equal(out.labels.cpu(), child)
+    np.testing.assert_allclose(out.eigvals[:, 0].cpu().numpy(), eigvals[:, 0].numpy(), rtol=RTOL)
+    for b in range(B):
+        assert torch.equal(canon(planted[b]), out.labels[b].cpu())
