@@ -42,7 +42,7 @@
 #ifndef EIG_PF         // 16-column blocks of A loaded together per lane in the matvec (one L2 round trip per batch)
 #define EIG_PF 3
 #endif
-#ifndef EIG_BATCH      // 1: load EIG_PF blocks together, then multiply them (see matvec_pass); 0: rolling window
+#ifndef EIG_BATCH      // 1: 128-thread CTAs load EIG_PF blocks together, then multiply them (see matvec_pass); 0: rolling window
 #define EIG_BATCH 1
 #endif
 #ifndef EIG_MINB       // CTAs per SM the register budget is sized for, at 128 threads
@@ -218,7 +218,7 @@ __device__ __forceinline__ void matvec_block(float (&acc)[TC][MT][4], const floa
 // TC consecutive 8-row tiles of A starting at tile0, all 16-column blocks: EIG_PF blocks in flight per lane (a
 // rolling register window, refilled right after a block's MMAs are issued), rows past the end are clamped
 // (their products are scaled by dinv = 0).
-template <int MT, int TC, bool FULL>
+template <int MT, int TC, bool FULL, bool BATCH>
 __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int lda, int n, int KB, bool last_ok,
                                             const float* __restrict__ uf, float* __restrict__ Yt,
                                             const float* __restrict__ dinv, int ldt, int rows, int tile0, int g,
@@ -240,7 +240,7 @@ __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int ld
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[q][mt][e] = 0.f;
   }
-#if EIG_BATCH
+  if constexpr (BATCH) {
   // batch mode: all global loads of a warp complete on one hardware scoreboard, so a rolling prefetch window
   // degenerates to one exposed L2 round trip per block.  Instead PF blocks are loaded together, then multiplied:
   // one round trip per PF blocks.
@@ -257,7 +257,8 @@ __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int ld
     for (int s = 0; s < PF; ++s)
       if (kb0 + s < KB) matvec_block<MT, TC, FULL>(acc, x[s], uf, kb0 + s);
   }
-#else
+  } else {
+  // rolling window (CTAs with many warps hide the round trips across warps; measured better at 512 threads)
 #pragma unroll
   for (int s = 0; s < PF; ++s) {
     const bool ok = s + 1 < KB || (s < KB && last_ok);
@@ -281,7 +282,7 @@ __device__ __forceinline__ void matvec_pass(const float* __restrict__ Ag, int ld
       }
     }
   }
-#endif
+  }
 #pragma unroll
   for (int q = 0; q < TC; ++q) {
     const int i = 8 * (tile0 + q) + 2 * t;
@@ -313,17 +314,18 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Ag, int lda, in
   // every 16-column block but the last lies inside the row; the last one is cut at lda (a multiple of 4)
   const bool last_ok = 16 * (KB - 1) + 4 * t < lda;
   const float* uf = Uf + lane * 4;
+  constexpr bool BATCH = EIG_BATCH != 0 && (NWARPS <= 4 || MT == 2);  // measured per configuration (profiles/r1c_summary.md)
   int tile0 = tbeg;
   for (; tile0 + T <= tend; tile0 += T)
-    matvec_pass<MT, T, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
+    matvec_pass<MT, T, FULL, BATCH>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
   const int left = tend - tile0;
   if constexpr (T > 3) {
-    if (left == 3) matvec_pass<MT, 3, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
+    if (left == 3) matvec_pass<MT, 3, FULL, BATCH>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
   }
   if constexpr (T > 2) {
-    if (left == 2) matvec_pass<MT, 2, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
+    if (left == 2) matvec_pass<MT, 2, FULL, BATCH>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
   }
-  if (left == 1) matvec_pass<MT, 1, FULL>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
+  if (left == 1) matvec_pass<MT, 1, FULL, BATCH>(Ag, lda, n, KB, last_ok, uf, Yt, dinv, ldt, rows, tile0, g, t);
 }
 
 // G[a][c] = sum_i dg[i] Q^T[a][i] Q^T[c][i]   and   H[a][c] = sum_i dg[i] P^T[a][i] Q^T[c][i]   (m x m, row
@@ -918,7 +920,9 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
       PHASE_END(PH_GRAMS);
       const bool scheduled = last || (it % P.rr_every) == 0;
       bool fired = false;
-      bool test = !scheduled && it >= 2 && it > P.fast_iters;
+      // the trigger is evaluated on scheduled iterations too: if the leading block has already converged, the exact
+      // leading-block step below finishes the segment instead of another approximate whole-block step
+      bool test = !last && it >= 2 && it > P.fast_iters;
       if (test) {
         // cheap screen: |y_c - U h_c|_D^2 + coupling = G_cc - sum_{a < kk} H_ac^2 up to rounding (U is D-orthonormal);
         // far above the tolerance (and the rounding floor) means not converged -- skip the explicit residuals
@@ -959,7 +963,7 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
         // ---- Rayleigh-Ritz: the whole block (scheduled; a few sweeps unless it is the last step), or only the
         //      leading columns once they span an invariant subspace (trigger; to full accuracy)
         int md = m, sweeps = last ? 12 : EIG_SWEEPS;
-        if (!scheduled) {
+        if (fired) {
           const int mdb = (kk + 1) & ~1;
           if (mdb <= me) { md = mdb; sweeps = 12; }
         }

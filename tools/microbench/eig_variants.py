@@ -73,7 +73,7 @@ def run(argv):
 
         def call():
             rc = fn(A.data_ptr(), deg.data_ptr(), V.data_ptr(), lam.data_ptr(), iters.data_ptr(), B * N, B, N, k, block, 60,
-                    float(os.environ.get("EIG_TOL", "2e-5")), 0.0, 0, None, None, st)
+                    float(os.environ.get("EIG_TOL", "2e-5")), 0.0, int(os.environ.get("EIG_NCONV", "0")), None, None, st)
             assert rc == 0, rc
         for _ in range(3):
             call()
