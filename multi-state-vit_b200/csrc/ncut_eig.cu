@@ -875,22 +875,22 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
       dg[i] = d;
       dinv[i] = d > 0.f ? 1.0f / d : 0.f;
     }
-    for (int e = threadIdx.x; e < rows * npad; e += THREADS) {
-      const int c = e / npad, i = e - c * npad;
-      float v = 0.f;
-      if (c < me && i < n) {
-        if (n <= m) v = (i == c) ? 1.f : 0.f;
-        else v = (c == 0) ? 1.f : hash_unit(i, c);
+    // one token per thread and step, all block rows in an inner loop (no index divisions); rows of the 16-row tiles
+    // beyond `rows` exist only in the fragment-order copy
+    for (int i = threadIdx.x; i < npad; i += THREADS) {
+#pragma unroll 4
+      for (int c = 0; c < MB; ++c) {
+        float v = 0.f;
+        if (c < me && i < n) {
+          if (n <= m) v = (i == c) ? 1.f : 0.f;
+          else v = (c == 0) ? 1.f : hash_unit(i, c);
+        }
+        if (c < rows) {
+          Ut[c * ldt + i] = v;
+          Yt[c * ldt + i] = 0.f;
+        }
+        Uf[uf_index<MT>(c, i)] = n > m ? v : 0.f;
       }
-      Ut[c * ldt + i] = v;
-      Yt[c * ldt + i] = 0.f;
-    }
-    // rows of the 16-row tiles beyond `rows` exist only in the fragment-order copy
-    for (int e = threadIdx.x; e < MB * npad; e += THREADS) {
-      const int c = e / npad, i = e - c * npad;
-      float v = 0.f;
-      if (c < me && i < n && n > m) v = (c == 0) ? 1.f : hash_unit(i, c);
-      Uf[uf_index<MT>(c, i)] = v;
     }
     __syncthreads();
 
@@ -1045,9 +1045,24 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n * k; e += THREADS) {
-      const int i = e / k, c = e - i * k;
-      Vout[e] = c < me ? Ut[c * ldt + i] * sqrtf(dg[i]) * res[c] : 0.f;
+    if ((k & 3) == 0 && (reinterpret_cast<uintptr_t>(P.V) & 15) == 0) {
+      // 4 consecutive columns of one token per thread: one sqrt and one 128-bit store (k % 4 == 0 keeps them aligned)
+      const int kq = k >> 2;
+      for (int e = threadIdx.x; e < n * kq; e += THREADS) {
+        const int i = e / kq, c = (e - i * kq) << 2;
+        const float sd = sqrtf(dg[i]);
+        float4 v;
+        v.x = c + 0 < me ? Ut[(c + 0) * ldt + i] * sd * res[c + 0] : 0.f;
+        v.y = c + 1 < me ? Ut[(c + 1) * ldt + i] * sd * res[c + 1] : 0.f;
+        v.z = c + 2 < me ? Ut[(c + 2) * ldt + i] * sd * res[c + 2] : 0.f;
+        v.w = c + 3 < me ? Ut[(c + 3) * ldt + i] * sd * res[c + 3] : 0.f;
+        *reinterpret_cast<float4*>(Vout + static_cast<size_t>(i) * k + c) = v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < n * k; e += THREADS) {
+        const int i = e / k, c = e - i * k;
+        Vout[e] = c < me ? Ut[c * ldt + i] * sqrtf(dg[i]) * res[c] : 0.f;
+      }
     }
     if (P.iters && threadIdx.x == 0) P.iters[s] = it;
     PHASE_END(PH_OUTPUT);
