@@ -715,12 +715,14 @@ __device__ __forceinline__ float cholesky_inverse(float* __restrict__ G, int m, 
 __device__ __forceinline__ void jacobi_rot(float app, float aqq, float apq, float& c, float& s, bool& big) {
   c = 1.f;
   s = 0.f;
-  const float scale = sqrtf(fabsf(app * aqq));
+  const float pq = fabsf(app * aqq);
+  const float scale = pq * rsqrtf(fmaxf(pq, 1e-37f));  // sqrt(|app aqq|), only used in the thresholds below
   const float aabs = fabsf(apq);
   if (aabs > 1e-30f && aabs > 1e-9f * scale) {
     const float delta = 0.5f * (aqq - app);
-    const float r = sqrtf(fmaf(delta, delta, apq * apq));
-    const float t = (delta >= 0.f ? apq : -apq) / (fabsf(delta) + r);
+    const float r2 = fmaf(delta, delta, apq * apq);
+    const float r = r2 * rsqrtf(r2);                    // r2 > 0 here; a 2-ulp root only perturbs the angle
+    const float t = __fdividef(delta >= 0.f ? apq : -apq, fabsf(delta) + r);
     c = rsqrtf(fmaf(t, t, 1.f));
     c = c * (1.5f - 0.5f * fmaf(t, t, 1.f) * c * c);  // one Newton step: c^2 + s^2 = 1 to fp32 accuracy
     s = t * c;
@@ -755,6 +757,9 @@ __device__ __forceinline__ void jacobi_impl(float* __restrict__ H, float* __rest
   sync();
   const int half = md >> 1;
   const int nb = half * half, ns = md * half;
+  // item -> (row pair / row, column pair): shifts when md / 2 is a power of two (the usual 16 and 8), else divisions
+  const bool pow2 = (half & (half - 1)) == 0;
+  const int hshift = 31 - __clz(half);
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     bool big = false;
     for (int r = 0; r < md - 1; ++r) {
@@ -775,7 +780,7 @@ __device__ __forceinline__ void jacobi_impl(float* __restrict__ H, float* __rest
       for (int item = tid; item < nb + ns; item += nthreads) {
         if (item < nb) {
           // H[P1][P2] <- J1^T H[P1][P2] J2
-          const int t1 = item / half, t2 = item - t1 * half;
+          const int t1 = pow2 ? item >> hshift : item / half, t2 = item - t1 * half;
           const float4 r1 = *reinterpret_cast<const float4*>(rot + 4 * t1);
           const float4 r2 = *reinterpret_cast<const float4*>(rot + 4 * t2);
           const int p1 = __float_as_int(r1.z), q1 = __float_as_int(r1.w);
@@ -790,7 +795,7 @@ __device__ __forceinline__ void jacobi_impl(float* __restrict__ H, float* __rest
         } else {
           // S[:, P2] <- S[:, P2] J2
           const int e = item - nb;
-          const int a = e / half, t2 = e - a * half;
+          const int a = pow2 ? e >> hshift : e / half, t2 = e - a * half;
           const float4 r2 = *reinterpret_cast<const float4*>(rot + 4 * t2);
           const int p2 = __float_as_int(r2.z), q2 = __float_as_int(r2.w);
           const float sp = Sm[a * ld + p2], sq = Sm[a * ld + q2];
