@@ -950,14 +950,16 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
       }
       if (test) {
         span_residuals<MT, NWARPS>(Hs, m, Ut, Yt, dg, kk, npad, ldt, rows, colred, res);
-        if (threadIdx.x == 0) {
+        if (warp == 0) {  // one wanted column per lane, then a warp maximum
           float worst = 0.f;
-          for (int c = 0; c < kk; ++c) {
+          for (int c = lane; c < kk; c += 32) {
             float v = res[c];
             for (int a = kk; a < me; ++a) v = fmaf(Hs[a * ld + c], Hs[a * ld + c], v);
             if (Hs[c * ld + c] >= P.lam_floor) worst = fmaxf(worst, v);
           }
-          misc[2] = worst <= tol2 ? 1.f : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+          if (lane == 0) misc[2] = worst <= tol2 ? 1.f : 0.f;
         }
         __syncthreads();
         fired = misc[2] != 0.f;
@@ -992,16 +994,18 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
         }
         __syncthreads();
         for (int e = threadIdx.x; e < m * m; e += THREADS) {
-          const int c = e / m, a = e - c * m;
+          const int c = (m & (m - 1)) == 0 ? e >> (31 - __clz(m)) : e / m, a = e - c * m;
           Ws[c * ld + a] = (c < md && a < md) ? Ss[a * ld + order[c]] : (a == c ? 1.f : 0.f);
         }
         __syncthreads();
         rotate<MT, NWARPS>(Ws, m, Ut, Yt, dg, theta, kk, npad, ldt, rows, colred, res);
-        if (threadIdx.x == 0) {
+        if (warp == 0) {
           float worst = 0.f;
-          for (int c = 0; c < kk; ++c)
+          for (int c = lane; c < kk; c += 32)
             if (theta[c] >= P.lam_floor) worst = fmaxf(worst, res[c]);
-          misc[1] = worst;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+          if (lane == 0) misc[1] = worst;
         }
         __syncthreads();
         PHASE_END(PH_ROTATE);
