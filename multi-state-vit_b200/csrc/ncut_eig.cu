@@ -61,7 +61,7 @@
 #define EIG_REORTH 1e-3f
 #endif
 #ifndef EIG_FAST_ITERS // leading products done in a single TF32 pass
-#define EIG_FAST_ITERS 2
+#define EIG_FAST_ITERS 3
 #endif
 
 namespace msvit {
