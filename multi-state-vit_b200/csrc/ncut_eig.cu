@@ -26,7 +26,7 @@
 //                                to the trailing ones (ordered iteration): fires the Rayleigh-Ritz step
 //     Rayleigh-Ritz              parallel-order Jacobi (rotations computed once per round, 2 x 2 blocks updated
 //                                in place), then [U; Y] <- W [U; Y] and the true residuals |Abar v - theta v|.
-//                                Scheduled every rr_every-th iteration on the whole m x m H with a few sweeps
+//                                Scheduled every rr_every-th (4th) iteration on the whole m x m H with a few sweeps
 //                                (the span does not change, only its basis); when the trigger fires, on the
 //                                leading block only, to full accuracy.
 //     U^T = L^-1 Y^T, L L^T = G  Cholesky QR in the D inner product (register Cholesky and explicit L^-1 on
