@@ -85,7 +85,7 @@ extern "C" int msvit_attention_mask(const int64_t* cluster_indices, uint8_t* mas
   if (B == 0) return MSVIT_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t L = static_cast<size_t>(2) * C + N;
-  const size_t per_block = 256 * 4 * 8;  // ~8 words per thread
+  const size_t per_block = 256 * 4 * 32;  // ~32 words per thread: the per-block label load and reduction amortise
   int gx = static_cast<int>((L * L + per_block - 1) / per_block);
   if (gx < 1) gx = 1;
   if (gx > 1024) gx = 1024;
