@@ -1102,6 +1102,9 @@ static int launch(const Params& P, cudaStream_t stream) {
 
 template <int MT>
 static int launch_threads(const Params& P, cudaStream_t stream) {
+#ifdef EIG_FORCE_THREADS
+  return launch<MT, EIG_FORCE_THREADS>(P, stream);
+#endif
   if (P.N <= 256) return launch<MT, 128>(P, stream);
   if (P.N <= 512) return launch<MT, 256>(P, stream);
   return launch<MT, 512>(P, stream);
