@@ -81,6 +81,28 @@ int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32
                    int N, int k, int block, int max_iter, float tol, float lam_floor, int n_converge,
                    const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream);
 
+/* Fused affinity + NCut subspace iteration for whole images of N <= 224 tokens (uniform segments, N > block):
+ * the affinity is produced and consumed in tensor memory and never written to global memory.
+ * Replaces NCUT.fit_transform as msvit_affinity_degree + msvit_ncut_eig do (same call sites, sandbox/test.py:108-118);
+ * the Rayleigh-Ritz rotation of the result is done by msvit_ritz_kmeans.
+ * x [S*N, D] tokens (MSVIT_F32 | MSVIT_BF16), deg [S*N] NCut degree (out),
+ * U [S*N, 16] D-orthonormal basis of the converged subspace (out, 16-byte aligned),
+ * H [S, 16, 16] projected operator U^T A U (out), iters [S], info [S] (1 = the leading n_converge columns met `tol`,
+ * 0 = stopped at max_iter).  block must be 16. */
+int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U, float* H, int32_t* iters, int32_t* info,
+                     int64_t total_rows, int S, int N, int D, int mode, float gamma, float scale, int block,
+                     int max_iter, float tol, float lam_floor, int n_converge, msvit_stream_t stream);
+
+/* Rayleigh-Ritz finish of msvit_ncut_fused + the k-means of msvit_kmeans in one kernel (uniform segments):
+ * V [S*N, k] eigenvectors (eigenvalues descending, sign canonical), lam [S, k]; then Lloyd k-means on V[:, :K] with
+ * K = n_clusters > 0 ? n_clusters : max(1, #{lam > eig_threshold}) (modeling_spectral.py:87-93), seeded from the
+ * row of largest degree.  labels [S*N] int32 and / or child [S*N] int64 (canonical ids; either may be NULL),
+ * n_child [S]. */
+int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* info, const float* deg, float* V, float* lam,
+                      int32_t* labels, int64_t* child, int32_t* n_child, int64_t total_rows, int S, int N, int k,
+                      int block, int n_converge, int n_clusters, float eig_threshold, int max_iter,
+                      msvit_stream_t stream);
+
 /* Lloyd k-means on the leading columns of the spectral embedding, per segment.
  * Replaces cuml KMeans(n_clusters).fit_predict(ncut_x[:, :n_child]) (modeling_spectral.py:90), the
  * seeded variants (:130-133, :277-278) and n_child = sum(eigenvalues > threshold) (:87,92-93).

@@ -17,8 +17,7 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = row-norm accumulation while the k-loop runs, then the epilogue.
-#include "common.cuh"
-#include "sm100_ptx.cuh"
+#include "tile_ops.cuh"
 
 namespace msvit {
 
@@ -64,39 +63,6 @@ struct Shared {
   // per lane in 32 different rows
   alignas(16) float stage[kEpiThreads / 32][32 * 20];
 };
-
-// Sum of squares of one 128-byte row of a k-slice as the tensor core sees it.
-// fp32 rows are first rounded to TF32 (round to nearest, in place): the tensor core would otherwise TRUNCATE
-// the low 13 mantissa bits, which shrinks every distance by ~1e-3 relative (a bias, not noise).
-template <bool TF32>
-__device__ __forceinline__ float row_sumsq(uint8_t* row, int lane) {
-  float acc = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    // rotate the 16-byte chunk order by lane so that the 8 lanes of a phase hit distinct bank groups
-    uint4* qp = reinterpret_cast<uint4*>(row + (((c + lane) & 7) << 4));
-    const uint4 q = *qp;
-    uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    if constexpr (TF32) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = (w[i] + 0x1000u) & 0xFFFFE000u;
-      *qp = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if constexpr (TF32) {
-        const float v = __uint_as_float(w[i]);
-        acc = fmaf(v, v, acc);
-      } else {
-        const float lo = __uint_as_float(w[i] << 16);
-        const float hi = __uint_as_float(w[i] & 0xFFFF0000u);
-        acc = fmaf(lo, lo, acc);
-        acc = fmaf(hi, hi, acc);
-      }
-    }
-  }
-  return acc;
-}
 
 // Per-row quantity cached for the epilogue.
 __device__ __forceinline__ float row_quantity(int mode, float sumsq, float c2) {
@@ -346,31 +312,6 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  return reinterpret_cast<EncodeTiledFn>(fn);
-}
-
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* x, bool f32, int64_t rows, int D, int box_rows) {
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * (f32 ? 4 : 2)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(f32 ? 32 : 64), static_cast<cuuint32_t>(box_rows)};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                         const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? MSVIT_OK : MSVIT_ERR_DRIVER;
 }
 
 }  // namespace aff

@@ -14,8 +14,7 @@
 //                         loads, fixed reduction order; emits the packed [k, D + 1] buffer (sums | count) that the
 //                         host all-reduces over NCCL when the rows are sharded
 //   msvit_gkm_finalize    centroid = sum / count (an empty cluster keeps its centre), fp32 master + operand copy
-#include "common.cuh"
-#include "sm100_ptx.cuh"
+#include "tile_ops.cuh"
 
 namespace msvit {
 namespace gkm {
@@ -49,37 +48,6 @@ struct Shared {
   float bests[2][kTile];
   int besti[2][kTile];
 };
-
-// Sum of squares of one 128-byte row of a k-slice as the tensor core sees it; fp32 rows are rounded to TF32
-// (nearest) in place first, because the tensor core would otherwise truncate them.
-template <bool TF32>
-__device__ __forceinline__ float row_sumsq(uint8_t* row, int lane) {
-  float acc = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4* qp = reinterpret_cast<uint4*>(row + (((c + lane) & 7) << 4));
-    const uint4 q = *qp;
-    uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    if constexpr (TF32) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = (w[i] + 0x1000u) & 0xFFFFE000u;
-      *qp = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if constexpr (TF32) {
-        const float v = __uint_as_float(w[i]);
-        acc = fmaf(v, v, acc);
-      } else {
-        const float lo = __uint_as_float(w[i] << 16);
-        const float hi = __uint_as_float(w[i] & 0xFFFF0000u);
-        acc = fmaf(lo, lo, acc);
-        acc = fmaf(hi, hi, acc);
-      }
-    }
-  }
-  return acc;
-}
 
 // Item = 256 rows of x against all centroids, walked in column blocks of 256 centroids.  Job (item, nt): a 256 x 256
 // score tile as two M=128 UMMA tiles in the two halves of TMEM.
@@ -256,31 +224,6 @@ assign_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  return reinterpret_cast<EncodeTiledFn>(fn);
-}
-
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* x, bool f32, int64_t rows, int D) {
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * (f32 ? 4 : 2)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(f32 ? 32 : 64), 128u};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                         const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? MSVIT_OK : MSVIT_ERR_DRIVER;
 }
 
 // ----------------------------------------------------------------------------- stable counting sort by label
@@ -460,9 +403,9 @@ extern "C" int msvit_gkm_assign(const void* x, int x_dtype, const void* centroid
   P.k_step = f32 ? 32 : 64;
   P.n_kslices = ceil_div(D, P.k_step);
   CUtensorMap tm_x, tm_c;
-  int rc = make_map(enc, &tm_x, x, f32, n, D);
+  int rc = make_map(enc, &tm_x, x, f32, n, D, 128);
   if (rc != MSVIT_OK) return rc;
-  rc = make_map(enc, &tm_c, centroids_op, f32, k, D);
+  rc = make_map(enc, &tm_c, centroids_op, f32, k, D, 128);
   if (rc != MSVIT_OK) return rc;
   const size_t smem = 1024 + static_cast<size_t>(kStages) * kStageBytes + sizeof(Shared);
   const int n_items = ceil_div(P.n, kTile);

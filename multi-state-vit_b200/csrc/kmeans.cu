@@ -10,7 +10,7 @@
 // so a warp reads it without bank conflicts).  Distance + argmin run in one pass per point; the centre update is a
 // segmented, atomic-free sum in a fixed order (thread (c, d, h) adds the members of cluster c in ascending token
 // order over half h of the tokens, the halves are combined in a fixed order).
-#include "common.cuh"
+#include "eig_core.cuh"
 
 namespace msvit {
 namespace km {
@@ -29,6 +29,14 @@ struct Params {
   const int32_t* seg_off;
   int S, N, ldv, n_clusters, Kmax, max_iter;
   float thr;
+  // Rayleigh-Ritz front end (ritz_kmeans_kernel only)
+  const float* U;        // [rows, 16] D-orthonormal basis from ncut_fused_kernel
+  const float* H;        // [S, 16, 16] projected operator
+  const int32_t* info;   // [S] 1 = leading block converged
+  float* Vout;           // [rows, ldv] eigenvectors (sign canonical)
+  float* lam_out;        // [S, ldv]
+  int64_t* child;        // [rows] int64 labels (single parent: child id = canonical cluster id), may be NULL
+  int m, kconv;
 };
 
 // block-wide argmax of (value, index) with ties -> lowest index; result broadcast to all threads
@@ -63,46 +71,44 @@ __device__ __forceinline__ float sqdist(const float* __restrict__ pt, int ldp, i
   return d;
 }
 
-__global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
-  extern __shared__ __align__(16) float smem[];
-  float* cen = smem;                                   // [kMaxK][kMaxK + 1]
-  float* mind = cen + kMaxK * (kMaxK + 1);             // [N]
-  int* lab = reinterpret_cast<int*>(mind + P.N);       // [N]
-  int* map = lab + P.N;                                // [kMaxK]
-  float* part = reinterpret_cast<float*>(map + kMaxK); // [2][kMaxK * kMaxK] partial centre sums
-  int* pcnt = reinterpret_cast<int*>(part + 2 * kMaxK * kMaxK);  // [2][kMaxK] partial counts
-  float* pts = reinterpret_cast<float*>(pcnt + 2 * kMaxK);       // [Kcap][ldp] transposed embedding
-  const int ldp = P.N | 1;                             // odd row stride
-  __shared__ float sval[kThreads / 32];
-  __shared__ int sidx[kThreads / 32];
-  __shared__ int s_changed;
-  constexpr int LDC = kMaxK + 1;
+// Shared-memory arrays of one segment's k-means (carved from dynamic shared memory by both kernels).
+struct Work {
+  float* cen;    // [kMaxK][kMaxK + 1]
+  float* mind;   // [N]
+  int* lab;      // [N]
+  int* map;      // [kMaxK]
+  float* part;   // [2][kMaxK * kMaxK] partial centre sums
+  int* pcnt;     // [2][kMaxK] partial counts
+  float* pts;    // [Kcap][ldp] transposed embedding
+  int ldp;
+  float* sval;   // [kThreads / 32]
+  int* sidx;     // [kThreads / 32]
+  int* changed;  // [1]
+};
+constexpr int LDC = kMaxK + 1;
 
-  for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
-    const int row0 = P.seg_off ? P.seg_off[s] : s * P.N;
-    const int n = P.seg_off ? P.seg_off[s + 1] - row0 : P.N;
-    if (n <= 0) {
-      if (threadIdx.x == 0) P.n_child[s] = 0;
-      continue;
-    }
-    const float* __restrict__ Pt = P.V + static_cast<long long>(row0) * P.ldv;
-    int K;
-    if (P.n_clusters > 0) {
-      K = P.n_clusters;
-    } else {
-      K = 0;
-      for (int j = 0; j < P.ldv; ++j) K += P.lam[static_cast<long long>(s) * P.ldv + j] > P.thr ? 1 : 0;
-      K = K < 1 ? 1 : K;
-    }
-    K = min(K, min(n, min(P.ldv, kMaxK)));
-    // stage the K leading coordinates of the segment's points (coalesced global reads, transposed writes)
-    __syncthreads();
-    for (int e = threadIdx.x; e < n * P.ldv; e += kThreads) {
-      const int i = e / P.ldv, j = e - i * P.ldv;
-      if (j < K) pts[j * ldp + i] = Pt[e];
-    }
-    __syncthreads();
+__device__ __forceinline__ Work carve(float* smem, int N, float* sval, int* sidx, int* changed) {
+  Work w;
+  w.cen = smem;
+  w.mind = w.cen + kMaxK * (kMaxK + 1);
+  w.lab = reinterpret_cast<int*>(w.mind + N);
+  w.map = w.lab + N;
+  w.part = reinterpret_cast<float*>(w.map + kMaxK);
+  w.pcnt = reinterpret_cast<int*>(w.part + 2 * kMaxK * kMaxK);
+  w.pts = reinterpret_cast<float*>(w.pcnt + 2 * kMaxK);
+  w.ldp = N | 1;  // odd row stride
+  w.sval = sval; w.sidx = sidx; w.changed = changed;
+  return w;
+}
 
+// Seeding, Lloyd iterations, canonical relabelling and the outputs of segment s; the K leading coordinates of its n
+// points are already staged in w.pts (transposed).
+__device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, int s, int row0, int n, int K) {
+  float* cen = w.cen; float* mind = w.mind; int* lab = w.lab; int* map = w.map; float* part = w.part; int* pcnt = w.pcnt;
+  float* pts = w.pts; float* sval = w.sval; int* sidx = w.sidx;
+  const int ldp = w.ldp;
+  int& s_changed = *w.changed;
+  {
     // ---- seeding
     if (P.init) {
       for (int e = threadIdx.x; e < K * K; e += kThreads)
@@ -114,8 +120,8 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         for (int i = threadIdx.x; i < n; i += kThreads) {
-          const float w = P.weight[row0 + i];
-          if (w > bv) { bv = w; bi = i; }
+          const float wt = P.weight[row0 + i];
+          if (wt > bv) { bv = wt; bi = i; }
         }
         first = block_argmax(bv, bi, sval, sidx);
         if (first < 0 || first >= n) first = 0;
@@ -186,7 +192,10 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
       P.n_child[s] = next;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kThreads) P.labels[row0 + i] = map[lab[i]];
+    if (P.labels)
+      for (int i = threadIdx.x; i < n; i += kThreads) P.labels[row0 + i] = map[lab[i]];
+    if (P.child)
+      for (int i = threadIdx.x; i < n; i += kThreads) P.child[row0 + i] = map[lab[i]];
     if (P.centres) {
       float* co = P.centres + static_cast<long long>(s) * P.Kmax * P.Kmax;
       for (int e = threadIdx.x; e < P.Kmax * P.Kmax; e += kThreads) co[e] = 0.f;
@@ -197,6 +206,152 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
       }
     }
     __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int select_k(const Params& P, const float* __restrict__ lam, int n) {
+  int K;
+  if (P.n_clusters > 0) {
+    K = P.n_clusters;
+  } else {
+    K = 0;
+    for (int j = 0; j < P.ldv; ++j) K += lam[j] > P.thr ? 1 : 0;
+    K = K < 1 ? 1 : K;
+  }
+  return min(K, min(n, min(P.ldv, kMaxK)));
+}
+
+__global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float sval[kThreads / 32];
+  __shared__ int sidx[kThreads / 32];
+  __shared__ int s_changed;
+  const Work w = carve(smem, P.N, sval, sidx, &s_changed);
+
+  for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
+    const int row0 = P.seg_off ? P.seg_off[s] : s * P.N;
+    const int n = P.seg_off ? P.seg_off[s + 1] - row0 : P.N;
+    if (n <= 0) {
+      if (threadIdx.x == 0) P.n_child[s] = 0;
+      continue;
+    }
+    const float* __restrict__ Pt = P.V + static_cast<long long>(row0) * P.ldv;
+    const int K = select_k(P, P.lam ? P.lam + static_cast<long long>(s) * P.ldv : nullptr, n);
+    // stage the K leading coordinates of the segment's points (coalesced global reads, transposed writes)
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * P.ldv; e += kThreads) {
+      const int i = e / P.ldv, j = e - i * P.ldv;
+      if (j < K) w.pts[j * w.ldp + i] = Pt[e];
+    }
+    __syncthreads();
+    kmeans_segment(P, w, s, row0, n, K);
+  }
+}
+
+// Rayleigh-Ritz finish of ncut_fused_kernel + k-means, one CTA per image (uniform segments of N tokens, N > m):
+//   H_lead = W Theta W^T (Jacobi; the leading kconv columns if they converged as a block, else the whole block),
+//   V = D^1/2 U W, eigenvalues descending, canonical sign (largest-|entry| positive, ties -> lowest row), then the
+//   k-means of kmeans_kernel on the embedding that is already in shared memory.
+__global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
+  using G = ThreadGroup<0, kThreads, 0>;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float sval[kThreads / 32];
+  __shared__ int sidx[kThreads / 32];
+  __shared__ int s_changed;
+  constexpr int MB = 16, LD = MB + 1;
+  __shared__ float Hm[MB * LD], Sm[MB * LD], Wm[MB * LD], theta[MB], sgn[MB], lam_s[MB];
+  __shared__ __align__(16) float rot[4 * (MB / 2)];   // jacobi() stores the rotations as float4
+  __shared__ int order[MB];
+  const Work w = carve(smem, P.N, sval, sidx, &s_changed);
+  const int n = P.N, m = P.m, k = P.ldv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
+    const int row0 = s * n;
+    __syncthreads();
+    for (int e = threadIdx.x; e < MB * MB; e += kThreads) Hm[(e >> 4) * LD + (e & 15)] = P.H[static_cast<size_t>(s) * 256 + e];
+    __syncthreads();
+    const int kk = P.kconv < m ? P.kconv : m;
+    int md = m;
+    if (P.info[s]) {
+      const int mdb = (kk + 1) & ~1;
+      if (mdb <= m) md = mdb;
+    }
+    eig::jacobi<G>(Hm, Sm, LD, md, 12, rot);
+    if (threadIdx.x < m) {
+      const int a = threadIdx.x;
+      const float ta = Hm[a * LD + a];
+      if (a < md) {
+        int rank = 0;
+        for (int b = 0; b < md; ++b) {
+          const float tb = Hm[b * LD + b];
+          rank += (tb > ta || (tb == ta && b < a)) ? 1 : 0;
+        }
+        order[rank] = a;
+        theta[rank] = ta;
+      } else {
+        order[a] = a;
+        theta[a] = ta;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += kThreads) {
+      const int c = e / m, a = e - c * m;
+      Wm[c * LD + a] = (c < md && a < md) ? Sm[a * LD + order[c]] : (a == c ? 1.f : 0.f);
+    }
+    __syncthreads();
+    // v_c(i) = sqrt(d_i) sum_a W[c][a] u_a(i): one token per thread and step, the basis row straight from global memory
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      const float4* up = reinterpret_cast<const float4*>(P.U + static_cast<size_t>(row0 + i) * MB);
+      const float4 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
+      const float u[16] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w, u2.x, u2.y, u2.z, u2.w, u3.x, u3.y, u3.z, u3.w};
+      const float sd = sqrtf(P.weight[row0 + i]);
+      for (int c = 0; c < k; ++c) {
+        float v = 0.f;
+        if (c < m) {
+#pragma unroll
+          for (int a = 0; a < 16; ++a) v = fmaf(Wm[c * LD + a], u[a], v);
+        }
+        w.pts[c * w.ldp + i] = v * sd;
+      }
+    }
+    __syncthreads();
+    // canonical sign per column (one warp per column), eigenvalues
+    for (int c = warp; c < k; c += kThreads / 32) {
+      float best = -1.f, bval = 0.f;
+      int bidx = 0x7fffffff;
+      for (int i = lane; i < n; i += 32) {
+        const float v = w.pts[c * w.ldp + i];
+        const float av = fabsf(v);
+        if (av > best) { best = av; bidx = i; bval = v; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        const float ov = __shfl_xor_sync(0xffffffffu, bval, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
+      }
+      if (lane == 0) {
+        sgn[c] = bval < 0.f ? -1.f : 1.f;
+        lam_s[c] = c < m ? theta[c] : 0.f;
+        P.lam_out[static_cast<size_t>(s) * k + c] = lam_s[c];
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * k; e += kThreads) {
+      const int i = e / k, c = e - i * k;
+      const float v = w.pts[c * w.ldp + i] * sgn[c];
+      P.Vout[static_cast<size_t>(row0) * k + e] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * k; e += kThreads) {
+      const int c = e / n, i = e - c * n;
+      w.pts[c * w.ldp + i] *= sgn[c];
+    }
+    __syncthreads();
+    const int K = select_k(P, lam_s, n);
+    kmeans_segment(P, w, s, row0, n, K);
   }
 }
 
@@ -220,6 +375,8 @@ extern "C" int msvit_kmeans(const float* V, const float* lam, const float* weigh
   P.centres = centres; P.seg_off = seg_off;
   P.S = S; P.N = N; P.ldv = ldv; P.n_clusters = n_clusters; P.Kmax = n_clusters > 0 ? n_clusters : ldv;
   P.max_iter = max_iter; P.thr = eig_threshold;
+  P.U = nullptr; P.H = nullptr; P.info = nullptr; P.Vout = nullptr; P.lam_out = nullptr; P.child = nullptr;
+  P.m = 0; P.kconv = 0;
   const int kcap = P.Kmax < kMaxK ? P.Kmax : kMaxK;   // coordinates staged per point
   const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N + 2 * kMaxK * kMaxK + static_cast<size_t>(kcap) * (N | 1)) +
                       sizeof(int) * (N + kMaxK + 2 * kMaxK);
@@ -228,5 +385,36 @@ extern "C" int msvit_kmeans(const float* V, const float* lam, const float* weigh
   if (e != cudaSuccess) return cuda_status(e);
   const int grid = S < 16 * sm_count() ? S : 16 * sm_count();
   kmeans_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(P);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* info, const float* deg, float* V,
+                                 float* lam, int32_t* labels, int64_t* child, int32_t* n_child, int64_t total_rows,
+                                 int S, int N, int k, int block, int n_converge, int n_clusters, float eig_threshold,
+                                 int max_iter, msvit_stream_t stream_) {
+  using namespace msvit;
+  using namespace msvit::km;
+  if (!U || !H || !info || !deg || !V || !lam || !n_child) return MSVIT_ERR_NULL;
+  if (!labels && !child) return MSVIT_ERR_NULL;
+  if (S < 0 || N <= 0 || k <= 0 || total_rows < 0 || max_iter <= 0) return MSVIT_ERR_SHAPE;
+  if (block != 16 || k > block || N <= block || n_converge < 0 || n_converge > block) return MSVIT_ERR_SHAPE;
+  if (n_clusters > k) return MSVIT_ERR_SHAPE;
+  if (total_rows != static_cast<int64_t>(S) * N) return MSVIT_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(U) & 15) != 0) return MSVIT_ERR_ALIGN;
+  if (S == 0) return MSVIT_OK;
+  Params P;
+  P.V = nullptr; P.lam = nullptr; P.weight = deg; P.init = nullptr; P.labels = labels; P.n_child = n_child;
+  P.centres = nullptr; P.seg_off = nullptr;
+  P.S = S; P.N = N; P.ldv = k; P.n_clusters = n_clusters; P.Kmax = n_clusters > 0 ? n_clusters : k;
+  P.max_iter = max_iter; P.thr = eig_threshold;
+  P.U = U; P.H = H; P.info = info; P.Vout = V; P.lam_out = lam; P.child = child;
+  P.m = block; P.kconv = n_converge > 0 ? n_converge : k;
+  const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N + 2 * kMaxK * kMaxK + static_cast<size_t>(k) * (N | 1)) +
+                      sizeof(int) * (N + kMaxK + 2 * kMaxK);
+  if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(ritz_kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_status(e);
+  const int grid = S < 16 * sm_count() ? S : 16 * sm_count();
+  ritz_kmeans_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(P);
   return cuda_status(cudaGetLastError());
 }

@@ -31,6 +31,10 @@ _SIGNATURES = {
                                        _c_f32, _c_ptr, _c_ptr, _c_ptr]),
     "msvit_ncut_eig": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_f32, _c_f32, _c_int, _c_ptr, _c_ptr, _c_ptr]),
+    "msvit_ncut_fused": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int,
+                                  _c_int, _c_f32, _c_f32, _c_int, _c_int, _c_f32, _c_f32, _c_int, _c_ptr]),
+    "msvit_ritz_kmeans": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int,
+                                   _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_ptr]),
     "msvit_kmeans": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int,
                               _c_int, _c_f32, _c_int, _c_ptr, _c_ptr]),
     "msvit_pool": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr]),

@@ -31,6 +31,15 @@ class ClusterOutput:
     affinity: Optional[torch.Tensor] = None  # [B, N, N] fp32 (single-parent case with N % 4 == 0 only)
 
 
+FUSED_BLOCK = 16     # subspace width of the fused kernel
+FUSED_MAX_TOKENS = 224
+
+
+def fused_eligible(N: int, block: int, n_parents: int = 1) -> bool:
+    """Shapes msvit_ncut_fused takes: whole images, 16 < N, round16(N) <= 224, subspace width 16."""
+    return n_parents == 1 and block == FUSED_BLOCK and FUSED_BLOCK < N and ((N + 15) & ~15) <= FUSED_MAX_TOKENS
+
+
 def default_block(k: int, oversample: int = 8) -> int:
     """Subspace width: k wanted + oversampling, multiple of 4, at most MAX_EIG_BLOCK."""
     m = (k + oversample + 3) & ~3
@@ -55,7 +64,7 @@ class ClusterPlan:
                  n_clusters: Optional[int] = None, eigenvalue_threshold: Optional[float] = None, mode: str = "rbf",
                  gamma: float = 3.0, scale: Optional[float] = None, n_parents: int = 1, kmeans_iters: int = 100,
                  eig_iters: int = 60, eig_tol: float = 2e-5, oversample: int = 8, pool_k: Optional[int] = None,
-                 want_pool: bool = True):
+                 want_pool: bool = True, fused: Optional[bool] = None):
         if mode not in _lib.DIST:
             raise ValueError(f"unknown distance {mode!r}")
         if n_clusters is None and eigenvalue_threshold is None:
@@ -85,13 +94,19 @@ class ClusterPlan:
         self.Kp = int(pool_k) if pool_k is not None else self.P * (self.nk if self.nk > 0 else self.k)
         B, N, D, P, k = self.B, self.N, self.D, self.P, self.k
         self.S = B * P
+        # whole images of up to 224 tokens take the fused kernel: the affinity stays in tensor memory
+        can_fuse = fused_eligible(N, self.block, P)
+        if fused and not can_fuse:
+            raise ValueError("the fused kernel needs whole images (one parent), 16 < tokens <= 224 and a subspace "
+                             "width of 16 (ncut_dim <= 8 with the default oversampling)")
+        self.fused = can_fuse if fused is None else bool(fused)
         rows = B * N
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             if P == 1:
                 self.perm = self.seg_off = self.a_off = self.xs = None
-                a_numel = rows * ops.lda_of(N)
+                a_numel = 0 if self.fused else rows * ops.lda_of(N)
             else:
                 self.perm = torch.empty(rows, **i32)
                 self.seg_off = torch.empty(self.S + 1, **i32)
@@ -108,6 +123,10 @@ class ClusterPlan:
             self.child = torch.empty(B, N, dtype=torch.int64, device=dev)
             self.pooled = torch.empty(B, self.Kp, D, **f32) if want_pool else None
             self.counts = torch.empty(B, self.Kp, **i32) if want_pool else None
+            if self.fused:
+                self.U = torch.empty(rows, FUSED_BLOCK, **f32)
+                self.H = torch.empty(self.S, FUSED_BLOCK * FUSED_BLOCK, **f32)
+                self.info = torch.empty(self.S, **i32)
 
     def run(self, x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, events=None) -> "ClusterOutput":
         """Enqueue the hot path for x [B, N, D].  `events`, if given, is a list of len(STAGES)+1 CUDA events that
@@ -142,20 +161,32 @@ class ClusterPlan:
             else:
                 xs = x
             mark(1)
-            check(lib.msvit_affinity_degree(p(xs), self.dtype_code, p(self.A), p(self.deg), rows, S, N, D, self.mode,
-                                            self.gamma, self.scale, p(self.seg_off), p(self.a_off), st),
-                  "msvit_affinity_degree")
-            mark(2)
-            check(lib.msvit_ncut_eig(p(self.A), p(self.deg), p(self.V), p(self.lam), p(self.iters), rows, S, N, k,
-                                     self.block, self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge,
-                                     p(self.seg_off), p(self.a_off), st), "msvit_ncut_eig")
-            mark(3)
-            check(lib.msvit_kmeans(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted), p(self.n_child),
-                                   None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters, p(self.seg_off), st),
-                  "msvit_kmeans")
-            mark(4)
-            check(lib.msvit_compose_labels(p(self.labels_sorted), p(self.n_child), p(self.perm), p(self.seg_off),
-                                           p(self.child), B, N, P, st), "msvit_compose_labels")
+            if self.fused:
+                check(lib.msvit_ncut_fused(p(x), self.dtype_code, p(self.deg), p(self.U), p(self.H), p(self.iters),
+                                           p(self.info), rows, S, N, D, self.mode, self.gamma, self.scale, self.block,
+                                           self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge, st),
+                      "msvit_ncut_fused")
+                mark(2)
+                mark(3)
+                check(lib.msvit_ritz_kmeans(p(self.U), p(self.H), p(self.info), p(self.deg), p(self.V), p(self.lam), None,
+                                            p(self.child), p(self.n_child), rows, S, N, k, self.block, self.n_converge,
+                                            self.nk, self.thr, self.kmeans_iters, st), "msvit_ritz_kmeans")
+                mark(4)
+            else:
+                check(lib.msvit_affinity_degree(p(xs), self.dtype_code, p(self.A), p(self.deg), rows, S, N, D, self.mode,
+                                                self.gamma, self.scale, p(self.seg_off), p(self.a_off), st),
+                      "msvit_affinity_degree")
+                mark(2)
+                check(lib.msvit_ncut_eig(p(self.A), p(self.deg), p(self.V), p(self.lam), p(self.iters), rows, S, N, k,
+                                         self.block, self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge,
+                                         p(self.seg_off), p(self.a_off), st), "msvit_ncut_eig")
+                mark(3)
+                check(lib.msvit_kmeans(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted), p(self.n_child),
+                                       None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters, p(self.seg_off), st),
+                      "msvit_kmeans")
+                mark(4)
+                check(lib.msvit_compose_labels(p(self.labels_sorted), p(self.n_child), p(self.perm), p(self.seg_off),
+                                               p(self.child), B, N, P, st), "msvit_compose_labels")
             mark(5)
             if self.want_pool:
                 check(lib.msvit_pool(p(x), self.dtype_code, p(self.child), p(self.pooled), p(self.counts), B, N, D,
@@ -170,7 +201,7 @@ class ClusterPlan:
             deg_tok[idx] = self.deg
         else:
             V_tok, deg_tok = self.V, self.deg
-        aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0) else None
+        aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0 and not self.fused) else None
         return ClusterOutput(labels=self.child, pooled=self.pooled, counts=self.counts, eigvecs=V_tok.view(B, N, k),
                              eigvals=self.lam.view(B, P, k), n_child=self.n_child.view(B, P),
                              degree=deg_tok.view(B, N), iters=self.iters.view(B, P), affinity=aff)
@@ -181,7 +212,7 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
                    mode: str = "rbf", gamma: float = 3.0, scale: Optional[float] = None,
                    n_parents: Optional[int] = None, kmeans_iters: int = 100, eig_iters: int = 60,
                    eig_tol: float = 2e-5, oversample: int = 8, pool_k: Optional[int] = None,
-                   want_pool: bool = True, keep_affinity: bool = False) -> ClusterOutput:
+                   want_pool: bool = True, keep_affinity: bool = False, fused: Optional[bool] = None) -> ClusterOutput:
     """One-shot form: builds a ClusterPlan for x's shape and runs it (buffers are owned by the result)."""
     if x.dim() != 3:
         raise ValueError("x must be [batch, tokens, hidden]")
@@ -200,7 +231,7 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
     plan = ClusterPlan(B, N, D, x.dtype, x.device, ncut_dim=ncut_dim, n_clusters=n_clusters,
                        eigenvalue_threshold=eigenvalue_threshold, mode=mode, gamma=gamma, scale=scale, n_parents=P,
                        kmeans_iters=kmeans_iters, eig_iters=eig_iters, eig_tol=eig_tol, oversample=oversample,
-                       pool_k=pool_k, want_pool=want_pool)
+                       pool_k=pool_k, want_pool=want_pool, fused=False if keep_affinity else fused)
     out = plan.run(x, parent_indices)
     if not keep_affinity:
         out.affinity = None
