@@ -9,9 +9,11 @@
 //   Y = D^-1 A U                     tcgen05.mma (TS form: A operand read from TMEM, kind::f16): A_hi [U_hi | U_lo] and
 //                                    A_lo U_hi accumulate into 32 more TMEM columns per tile; the block U (16 columns,
 //                                    fp16 hi/lo pair scaled by 2^10) is the K-major shared-memory operand
-//   G2 = Y^T D Y, H = U^T D Y        mma.sync TF32x3 on the transposed blocks in shared memory (eig_core.cuh)
-//   U = Y L^-T,  L L^T = G2          Cholesky QR in the D inner product: register Cholesky on one warp, forward
-//                                    substitution per token (thread = token, u and y live in registers)
+//   G2 = Y^T D Y, H = U^T D Y        one more tcgen05.mma chain: [Y_hi; Y_lo; U_hi; U_lo] (64 operand rows, K = tokens)
+//                                    times [DY_hi | DY_lo]; warp quadrant 0 reads G2, quadrant 1 reads H from TMEM
+//   U = Y L^-T,  L L^T = G2          Cholesky QR in the D inner product: the warp that read G2 factorises it in
+//                                    registers (lane = row), forward substitution per token (thread = token, u and y
+//                                    live in registers); meanwhile the warp that read H screens for convergence
 //   stop                             when the leading columns span an invariant subspace to the tolerance (or at the
 //                                    iteration cap); the Rayleigh-Ritz rotation of the result is left to the next
 //                                    kernel (kmeans.cu: ritz_kmeans_kernel), where hundreds of segments overlap
@@ -35,7 +37,7 @@ namespace fused {
 
 #ifdef FUSED_PROFILE
 // Development instrumentation: cycles the first compute thread of every CTA spends in each phase.
-enum { FP_GRAM, FP_EPI, FP_INIT, FP_UOP, FP_PRODUCT, FP_DRAIN, FP_GRAMS, FP_TRIGGER, FP_CHOL, FP_SUBST, FP_OUTPUT, FP_COUNT };
+enum { FP_GRAM, FP_EPI, FP_INIT, FP_UOP, FP_PRODUCT, FP_DRAIN, FP_GRAMS, FP_TRIGGER, FP_CHOL, FP_SUBST, FP_OUTPUT, FP_X1, FP_X2, FP_COUNT };
 __device__ unsigned long long g_fused_cycles[FP_COUNT];
 #define FPHASE_BEGIN() long long fp_t0 = clock64()
 #define FPHASE_END(ph)                                                                     \
@@ -56,10 +58,15 @@ constexpr int kSliceBytes = 128;
 constexpr int kMaxStages = 6;
 constexpr int kTmemCols = 512;
 constexpr int kMB = 16;               // subspace block width (columns of U)
-constexpr int kMaxT = 224;            // 2 * 224 + 64 accumulator columns fill the 512 of TMEM
-constexpr int kTileCols = 224;        // TMEM column stride of the two affinity tiles (a multiple of 32)
+constexpr int kMaxT = 208;            // 2 * 208 affinity columns + 96 accumulator columns fill the 512 of TMEM
+constexpr int kTileCols = 208;        // TMEM column stride of the two affinity tiles
 constexpr float kUScale = 1024.f;     // |u| <= 1 for a D-orthonormal block (deg >= 1): fp16 operands never overflow
-constexpr int kUopBytes = 4 * 32 * kSliceBytes;   // 4 k-slices of 64 tokens x 32 operand rows (U_hi | U_lo)
+constexpr float kDScale = 64.f;       // |deg * y| <= deg <= N before the first orthonormalisation, <= sqrt(deg) after
+constexpr int kOpARows = 64;          // operand block A per 64-token k-slice: rows [Y_hi; Y_lo; U_hi; U_lo] x 128 bytes
+constexpr int kOpBRows = 32;          // operand block B: rows [DY_hi; DY_lo]
+constexpr int kOpABytes = 4 * kOpARows * kSliceBytes;
+constexpr int kOpBBytes = 4 * kOpBRows * kSliceBytes;
+constexpr int kUopBytes = kOpABytes + kOpBBytes;
 using G = ThreadGroup<kComputeBase, kCompute, 1>;
 
 struct Params {
@@ -83,32 +90,27 @@ struct Shared {
   uint64_t conv[kMaxStages];
   uint64_t tmem_full;
   uint64_t tmem_empty;
-  uint64_t ybar;
+  uint64_t ybar;        // product accumulators complete (one commit per M tile)
+  uint64_t gbar;        // Gram accumulator complete
   uint32_t tmem_base;
   uint32_t pad;
   float rq[256];    // per-token quantity of the distance (row and column side are the same tokens)
 };
 
-// float offsets of the eigensolver's shared arrays
+// float offsets of the eigensolver's small shared arrays
 struct EigLayout {
-  int Ut, Yt, dg, Gs, Hs, LT, pinv, misc, colred, gscr, total;
-  int ldt;
+  int Gs, Hs, LT, pinv, misc, red, rowbuf, total;
 };
-__host__ __device__ inline EigLayout make_eig_layout(int N) {
+__host__ __device__ inline EigLayout make_eig_layout() {
   EigLayout L;
-  L.ldt = eig::ldt_of(N);
-  const int mm = round_up(kMB * (kMB + 1), 4);
   int o = 0;
-  L.Ut = o;      o += kMB * L.ldt;
-  L.Yt = o;      o += kMB * L.ldt;
-  L.dg = o;      o += 256;
-  L.Gs = o;      o += mm;
-  L.Hs = o;      o += mm;
+  L.Gs = o;      o += kMB * kMB;   // row stride 16: rows are read as 128-bit broadcast loads
+  L.Hs = o;      o += kMB * kMB;
   L.LT = o;      o += 256;
   L.pinv = o;    o += 16;
-  L.misc = o;    o += 8 + 3 * MSVIT_MAX_EIG_BLOCK;
-  L.colred = o;  o += (kCompute / 32) * MSVIT_MAX_EIG_BLOCK;
-  L.gscr = o;    o += (kCompute / 32) * 128;     // partial Gram tiles (weighted_grams splits the tokens over warps)
+  L.misc = o;    o += 8;
+  L.red = o;     o += (kCompute / 32) * 16;   // per-warp partial sums of the span residuals
+  L.rowbuf = o;  o += 32;                     // pivot rows of the Cholesky (16-byte aligned)
   L.total = o;
   return L;
 }
@@ -138,6 +140,16 @@ __device__ __forceinline__ void umma_ts_f16_elect(uint32_t d_tmem, uint32_t a_tm
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_ss_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
@@ -157,11 +169,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_constant__ CUtensorMap tm_tail,
                   const Params P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array itself, not on an integer: the compiler keeps the shared address space and
+  // emits LDS / STS instead of generic loads and stores for everything derived from it)
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* uop = tiles + static_cast<size_t>(P.stages) * P.stage_bytes;   // 1024-aligned (stage_bytes % 1024 == 0)
   Shared& sh = *reinterpret_cast<Shared*>(uop + kUopBytes);
   float* ef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&sh) + ((sizeof(Shared) + 15) & ~size_t(15)));
-  const EigLayout L = make_eig_layout(P.N);
+  const EigLayout L = make_eig_layout();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,6 +191,7 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
     mbar_init(&sh.tmem_full, 1);
     mbar_init(&sh.tmem_empty, kCompute / 32);
     mbar_init(&sh.ybar, n_tiles);
+    mbar_init(&sh.gbar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_full);
     tma_prefetch_desc(&tm_tail);
@@ -249,28 +264,108 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
     const bool valid = row < n;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t a_col = tile * kTileCols;    // this tile's affinity columns
-    const uint32_t y_col = 2 * kTileCols + 32 * tile;   // this tile's product accumulator
-    float* Ut = ef + L.Ut;
-    float* Yt = ef + L.Yt;
-    float* dg = ef + L.dg;
+    const uint32_t y_col = 2 * kTileCols + 32 * tile;   // this tile's product accumulator (32 columns: x_hi | x_lo)
     float* Gs = ef + L.Gs;
     float* Hs = ef + L.Hs;
     float* LT = ef + L.LT;
     float* pinv = ef + L.pinv;
-    float* misc = ef + L.misc;          // [0] scalar broadcast, [2] trigger flag
-    float* res = misc + 8 + MSVIT_MAX_EIG_BLOCK;
-    float* colred = ef + L.colred;
-    float* gscr = ef + L.gscr;
-    const int ldt = L.ldt;
-    const int m = P.m, ld = m + 1;
-    const int me = m;                   // n > m is required by the launcher
+    float* misc = ef + L.misc;          // [0] smallest scaled pivot, [2] trigger flag
+    float* red = ef + L.red;
+    float* rowbuf = ef + L.rowbuf;
+    constexpr int m = kMB, ld = kMB;    // the launcher only accepts a block width of 16 ...
+    constexpr int me = kMB;             // ... and more tokens than that
     const int kk = P.kconv < me ? P.kconv : me;
     const int npad = round_up(n, 16);
-    const int nks = npad >> 4;          // K = 16 steps of the product
+    const int nks = npad >> 4;          // K = 16 steps of every tensor-core contraction over the tokens
     const float tol2 = P.tol * P.tol;
     const uint32_t idesc32 = make_idesc(0u, 128u, 32u), idesc16 = make_idesc(0u, 128u, 16u);
-    const uint32_t uop_addr = smem_u32(uop);
-    uint32_t yphase = 0;
+    const uint32_t opa_addr = smem_u32(uop), opb_addr = opa_addr + kOpABytes;
+    const uint32_t g_col = 2 * kTileCols + 64;   // Gram accumulator (32 columns), in flight together with the product
+    uint32_t yphase = 0, gphase = 0;
+    // the warps that issue the products sit on different schedulers (warp % 4) than each other and than the Cholesky
+    // warp (4): warp 2 for M tile 0, warp 9 for M tile 1
+    const bool prod_issuer = (cw == 0) || (cw == 7 && n_tiles > 1);
+    // this thread's token inside the operand blocks: k-slice row >> 6, 16-byte chunk (kc >> 3) ^ (r & 7), 2 bytes at kc & 7
+    uint8_t* const opa_tok = uop + (row >> 6) * (kOpARows * kSliceBytes);
+    uint8_t* const opb_tok = uop + kOpABytes + (row >> 6) * (kOpBRows * kSliceBytes);
+    const int kc = row & 63;
+    // rows r0 .. r0+15 of an operand block <- fp16(scale * v), rows r0+16 .. r0+31 <- the fp16 remainder
+    auto store_rows = [&](uint8_t* blk, int r0, const float (&v)[16], float scale, bool with_lo) {
+      const int within = (kc & 7) * 2;
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        const float s0 = v[c] * scale, s1 = v[c + 1] * scale;
+        const float h0 = __uint_as_float(__float_as_uint(s0) & 0xffffe000u);
+        const float h1 = __uint_as_float(__float_as_uint(s1) & 0xffffe000u);
+        const uint32_t hh = pack_f16x2(h0, h1);
+        const int off0 = (((kc >> 3) ^ (c & 7)) << 4) + within;
+        const int off1 = (((kc >> 3) ^ ((c + 1) & 7)) << 4) + within;
+        *reinterpret_cast<uint16_t*>(blk + (r0 + c) * kSliceBytes + off0) = static_cast<uint16_t>(hh & 0xffffu);
+        *reinterpret_cast<uint16_t*>(blk + (r0 + c + 1) * kSliceBytes + off1) = static_cast<uint16_t>(hh >> 16);
+        if (with_lo) {
+          const uint32_t ll = pack_f16x2(s0 - h0, s1 - h1);
+          *reinterpret_cast<uint16_t*>(blk + (r0 + 16 + c) * kSliceBytes + off0) = static_cast<uint16_t>(ll & 0xffffu);
+          *reinterpret_cast<uint16_t*>(blk + (r0 + 17 + c) * kSliceBytes + off1) = static_cast<uint16_t>(ll >> 16);
+        }
+      }
+    };
+    // [X_hi; X_lo]^T D [X'_hi | X'_lo] over the tokens: operand rows a_row0 .. a_row0+31 of block A against block B,
+    // 32 accumulator columns at g_col; issued by one warp
+    auto issue_gram = [&](int a_row0) {
+      tc_fence_after();
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t koff = (ks >> 2) * (kOpARows * kSliceBytes) + (ks & 3) * 32;
+        const uint32_t boff = (ks >> 2) * (kOpBRows * kSliceBytes) + (ks & 3) * 32;
+        umma_ss_f16_elect(tmem_base + g_col, make_kmajor_sw128_desc(opa_addr + a_row0 * kSliceBytes + koff),
+                          make_kmajor_sw128_desc(opb_addr + boff), idesc32, ks ? 1u : 0u);
+      }
+      tc_commit_elect(&sh.gbar);
+    };
+    // Z = A X on the tensor cores for this warp's M tile: X = the operand rows b_row0 .. b_row0+15 (hi) and +16 .. +31
+    // (lo) of block A; A_hi [X_hi | X_lo] and A_lo X_hi (single pass A_hi X_hi unless `full`) -> the tile's 32 columns
+    auto issue_product = [&](int b_row0, bool full) {
+      tc_fence_after();
+      const uint32_t a0 = tmem_base + a_col, d0 = tmem_base + y_col;
+      const uint32_t xb = opa_addr + b_row0 * kSliceBytes;
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint64_t bd = make_kmajor_sw128_desc(xb + (ks >> 2) * (kOpARows * kSliceBytes) + (ks & 3) * 32);
+        umma_ts_f16_elect(d0, a0 + 16 * ks, bd, full ? idesc32 : idesc16, ks ? 1u : 0u);   // A_hi [x_hi | x_lo]
+      }
+      if (full) {
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t bd = make_kmajor_sw128_desc(xb + (ks >> 2) * (kOpARows * kSliceBytes) + (ks & 3) * 32);
+          umma_ts_f16_elect(d0, a0 + 16 * ks + 8, bd, idesc16, 1u);                          // A_lo x_hi
+        }
+      }
+      tc_commit_elect(&sh.ybar);
+    };
+    // this thread's row of the finished product, scaled to D^-1 A x
+    auto read_product = [&](float (&z)[16], float dinv_s, bool full) {
+      if (tile < n_tiles) {
+        float za[16];
+        tmem_ld16(lane_addr + y_col, za);
+        if (full) {
+          float zb[16];
+          tmem_ld16(lane_addr + y_col + 16, zb);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) za[c] += zb[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) z[c] = valid ? za[c] * dinv_s : 0.f;
+      }
+    };
+    // Accumulator rows 32 q .. 32 q + 31 (q = this warp's lane quadrant) hold [X_hi; X_lo] . [DX'_hi | DX'_lo]:
+    // lanes 0..15 return row `lane` of X^T D X' = hi.hi + hi.lo + lo.hi, unscaled
+    auto read_gram_rows = [&](float (&g)[16], float inv_scale) {
+      float v0[16], v1[16];
+      tmem_ld16(lane_addr + g_col, v0);
+      tmem_ld16(lane_addr + g_col + 16, v1);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float mine = lane < 16 ? v0[c] + v1[c] : v0[c];
+        g[c] = (mine + __shfl_down_sync(0xffffffffu, mine, 16)) * inv_scale;
+      }
+    };
 
     for (int s = blockIdx.x; s < P.S; s += gridDim.x, ++job) {
       const int row0 = s * n;
@@ -282,12 +377,8 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
         const uint32_t ph = (it_ring / P.stages) & 1;
         mbar_wait(&sh.full[st], ph);
         uint8_t* bt = tiles + static_cast<size_t>(st) * P.stage_bytes;
-        if (P.debug & 32) {   // timing experiment: no in-place rounding
-          if (ct < T) ss += row_sumsq<false>(bt + ct * kSliceBytes, lane);
-        } else {
-          if (ct < T) ss += row_sumsq<TF32>(bt + ct * kSliceBytes, lane);
-          if constexpr (TF32) fence_proxy_async_smem();  // the rounded tile must be visible to the tensor core
-        }
+        if (ct < T) ss += row_sumsq<TF32>(bt + ct * kSliceBytes, lane);
+        if constexpr (TF32) fence_proxy_async_smem();  // the rounded tile must be visible to the tensor core
         __syncwarp();
         if (lane == 0) {
           if constexpr (TF32) mbar_arrive(&sh.conv[st]);
@@ -329,7 +420,6 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
       if (valid) P.deg[row0 + row] = rowsum;
       const float d = valid ? rowsum : 0.f;
       const float dinv_s = (valid && rowsum > 0.f) ? (1.0f / kUScale) / rowsum : 0.f;  // 1 / (deg * operand scale)
-      dg[row] = d;    // every row 0..255 is owned by exactly one thread; pad tokens get 0
       FPHASE_END(FP_EPI);
 
       // ---- start block (same as ncut_eig.cu): column 0 constant, the rest pseudo-random; pad tokens zero
@@ -339,165 +429,207 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
         u[c] = (valid && c < me) ? (c == 0 ? 1.f : eig::hash_unit(static_cast<uint32_t>(row), static_cast<uint32_t>(c))) : 0.f;
         y[c] = 0.f;
       }
-      if (row < npad) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) Ut[c * ldt + row] = u[c];
-      }
 
       int it = 0;
       bool fired = false;
+      float z[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) z[c] = 0.f;
+      // ---- first product on the raw start block: y = D^-1 A u  (operand rows [U_hi; U_lo])
+      if (row < npad) store_rows(opa_tok, 32, u, kUScale, true);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      G::sync();
+      const bool full0 = (P.debug & 128) || P.fast_iters < 1;
+      if (prod_issuer) issue_product(32, full0);
+      mbar_wait(&sh.ybar, yphase);
+      yphase ^= 1;
+      tc_fence_after();
+      read_product(y, dinv_s, full0);
       FPHASE_END(FP_INIT);
+      // Invariant at the top of every iteration: y = D^-1 A u.  The iteration orthonormalises y (Cholesky QR in the D
+      // inner product) and, IN THE SHADOW of the Gram + Cholesky step, already multiplies the un-orthonormalised y
+      // by the operator: z = D^-1 A y, so that the next iterate's image is L^-1 z (the factor is triangular: the
+      // leading columns never see the small trailing ones).
       while ((P.debug & 15) != 1) {
         ++it;
-        const bool full = !(it <= P.fast_iters && it < P.max_iter);
-        // ---- shared-memory operand: rows 0..15 = fp16(2^10 u), rows 16..31 = the fp16 remainder; K-major, 128B swizzle
+        const bool last = it >= P.max_iter;
+        const bool test = !last && it >= 2 && it > P.fast_iters;
+        // ---- operand rows: [Y_hi; Y_lo] and [DY_hi; DY_lo]; [U_hi; U_lo] when H = U^T D Y is looked at
         if (row < npad) {
-          uint8_t* ob = uop + (row >> 6) * (32 * kSliceBytes);
-          const int kc = row & 63;
-          const int within = (kc & 7) * 2;
+          store_rows(opa_tok, 0, y, kUScale, true);
+          float dy[16];
 #pragma unroll
-          for (int c = 0; c < 16; c += 2) {
-            const float s0 = u[c] * kUScale, s1 = u[c + 1] * kUScale;
-            const float h0 = __uint_as_float(__float_as_uint(s0) & 0xffffe000u);
-            const float h1 = __uint_as_float(__float_as_uint(s1) & 0xffffe000u);
-            const uint32_t hh = pack_f16x2(h0, h1);
-            const int off0 = ((((kc >> 3) ^ (c & 7))) << 4) + within;
-            const int off1 = ((((kc >> 3) ^ ((c + 1) & 7))) << 4) + within;
-            *reinterpret_cast<uint16_t*>(ob + c * kSliceBytes + off0) = static_cast<uint16_t>(hh & 0xffffu);
-            *reinterpret_cast<uint16_t*>(ob + (c + 1) * kSliceBytes + off1) = static_cast<uint16_t>(hh >> 16);
-            if (full) {
-              const uint32_t ll = pack_f16x2(s0 - h0, s1 - h1);
-              *reinterpret_cast<uint16_t*>(ob + (16 + c) * kSliceBytes + off0) = static_cast<uint16_t>(ll & 0xffffu);
-              *reinterpret_cast<uint16_t*>(ob + (17 + c) * kSliceBytes + off1) = static_cast<uint16_t>(ll >> 16);
-            }
-          }
+          for (int c = 0; c < 16; ++c) dy[c] = d * y[c];
+          store_rows(opb_tok, 0, dy, kDScale, true);
+          if (test || last) store_rows(opa_tok, 32, u, kUScale, true);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         G::sync();
-        if ((P.debug & 15) == 2) break;
         FPHASE_END(FP_UOP);
-        // ---- Y = A U on the tensor cores (warps 2 and 6: one M tile each)
-        if ((cw & 3) == 0 && tile < n_tiles) {
+        // ---- tensor cores: G2 = Y^T D Y and H = U^T D Y (warp 3), z = A y (warps 2 and 6: one M tile each)
+        if (cw == 1) issue_gram(0);
+        const bool fulln = (P.debug & 128) || it + 1 > P.fast_iters;   // precision of the product that feeds iteration it + 1
+        if ((P.debug & 64) && prod_issuer) issue_product(0, fulln);   // development: issue before the Gram completes
+        // (only the warps that need a result wait on its mbarrier; the others block in the hardware barrier below and
+        // leave their scheduler's issue slots to the warps that work)
+        float grow[16];
+        if (q < 2 && tile == 0) {   // warp 4 (quadrant 0): G2, warp 5 (quadrant 1): H
+          mbar_wait(&sh.gbar, gphase);
           tc_fence_after();
-          const uint32_t a0 = tmem_base + a_col, d0 = tmem_base + y_col;
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t bd = make_kmajor_sw128_desc(uop_addr + (ks >> 2) * (32 * kSliceBytes) + (ks & 3) * 32);
-            umma_ts_f16_elect(d0, a0 + 16 * ks, bd, full ? idesc32 : idesc16, ks ? 1u : 0u);
+          read_gram_rows(grow, 1.0f / (kUScale * kDScale));
+          if (lane < 16) {
+            float4* dst = reinterpret_cast<float4*>((q == 0 ? Gs : Hs) + lane * ld);
+            dst[0] = make_float4(grow[0], grow[1], grow[2], grow[3]);
+            dst[1] = make_float4(grow[4], grow[5], grow[6], grow[7]);
+            dst[2] = make_float4(grow[8], grow[9], grow[10], grow[11]);
+            dst[3] = make_float4(grow[12], grow[13], grow[14], grow[15]);
           }
-          if (full) {
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t bd = make_kmajor_sw128_desc(uop_addr + (ks >> 2) * (32 * kSliceBytes) + (ks & 3) * 32);
-              umma_ts_f16_elect(d0, a0 + 16 * ks + 8, bd, idesc16, 1u);
-            }
-          }
-          tc_commit_elect(&sh.ybar);
         }
-        mbar_wait(&sh.ybar, yphase);
-        yphase ^= 1;
-        tc_fence_after();
-        FPHASE_END(FP_PRODUCT);
-        if (tile < n_tiles) {
-          float ya[16];
-          tmem_ld16(lane_addr + y_col, ya);
-          if (full) {
-            float yb[16];
-            tmem_ld16(lane_addr + y_col + 16, yb);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) ya[c] += yb[c];
-          }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) y[c] = valid ? ya[c] * dinv_s : 0.f;
-        }
-        if (row < npad) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) Yt[c * ldt + row] = y[c];
-        }
+        gphase ^= 1;
         tc_fence_before();
         G::sync();
-        FPHASE_END(FP_DRAIN);
-        if ((P.debug & 15) == 3) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) u[c] = y[c];
-          break;
-        }
-
-        const bool last = it >= P.max_iter;
-        // ---- G2 = Y^T D Y, H = U^T D Y
-        eig::weighted_grams<G>(Ut, Yt, dg, n, m, ldt, kMB, Gs, Hs, true, gscr);
         FPHASE_END(FP_GRAMS);
-        if ((P.debug & 15) == 4) break;
-        bool test = !last && it >= 2 && it > P.fast_iters;
-        if (test) {
-          // cheap screen (see ncut_eig.cu): G_cc - sum_{a < kk} H_ac^2 far above the tolerance means not converged
-          if (cw == 0) {
-            float v = 0.f;
-            for (int c = lane; c < kk; c += 32) {
-              const float gcc = Gs[c * ld + c];
-              float e = gcc;
-              for (int a = 0; a < kk; ++a) e = fmaf(-Hs[a * ld + c], Hs[a * ld + c], e);
-              e -= 64.f * tol2 + 8e-6f * gcc;
-              if (Hs[c * ld + c] >= P.lam_floor) v = fmaxf(v, e);
-            }
+        // (issued only now: product MMAs queued ahead of the Gram chain would delay the Cholesky by their length)
+        if (!(P.debug & (64 | 2048)) && prod_issuer) issue_product(0, fulln);
+        // ---- quadrant-0 warp: Cholesky of G2 in registers; quadrant-1 warp: cheap convergence screen on (G2, H)
+        if (q == 0 && tile == 0) {
+          float dorig = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (lane == 0) misc[2] = v > 0.f ? 0.f : 1.f;
+          for (int c = 0; c < 16; ++c) dorig = lane == c ? grow[c] : dorig;
+#ifdef FUSED_PROFILE
+          const long long xc0 = clock64();
+#endif
+          eig::cholesky_lt16_regs(grow, dorig, me, LT, pinv, misc, rowbuf);
+#ifdef FUSED_PROFILE
+          if (lane == 0) atomicAdd(&g_fused_cycles[FP_X1], (unsigned long long)(clock64() - xc0));
+#endif
+        } else if (q == 1 && tile == 0 && test) {
+          // G_cc - sum_{a < kk} H_ac^2 far above the tolerance means not converged (see ncut_eig.cu)
+          float v = 0.f;
+          for (int c = lane; c < kk; c += 32) {
+            const float gcc = Gs[c * ld + c];
+            float e = gcc;
+            for (int a = 0; a < kk; ++a) e = fmaf(-Hs[a * ld + c], Hs[a * ld + c], e);
+            e -= 64.f * tol2 + 8e-6f * gcc;
+            if (Hs[c * ld + c] >= P.lam_floor) v = fmaxf(v, e);
           }
-          G::sync();
-          test = misc[2] != 0.f;
-          G::sync();
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+          if (lane == 0) misc[2] = v > 0.f ? 0.f : 1.f;
         }
-        if (test) {
-          // |y_c - U h_c|_D^2 + coupling to the trailing columns, summed over the wanted columns: bounds the residual
-          // of every Ritz pair of the leading block
-          eig::span_residuals<1, G>(Hs, m, Ut, Yt, dg, kk, npad, ldt, kMB, colred, res);
-          if (cw == 0) {
-            float tot = 0.f;
-            for (int c = lane; c < kk; c += 32) {
-              float v = res[c];
-              for (int a = kk; a < me; ++a) v = fmaf(Hs[a * ld + c], Hs[a * ld + c], v);
-              if (Hs[c * ld + c] >= P.lam_floor) tot = (P.debug & 16) ? fmaxf(tot, v) : tot + v;
-            }
-            if (P.debug & 16) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) tot = fmaxf(tot, __shfl_xor_sync(0xffffffffu, tot, o));
-            } else {
-              tot = warp_sum(tot);
-            }
-            if (lane == 0) misc[2] = tot <= tol2 ? 1.f : 0.f;
-          }
+        FPHASE_END(FP_CHOL);
+#ifdef FUSED_PROFILE
+        const long long xp0 = clock64();
+#endif
+        if (P.debug & 2048) {   // development: product only after the Cholesky
           G::sync();
-          fired = misc[2] != 0.f;
+          if (prod_issuer) issue_product(0, fulln);
+        }
+        if (prod_issuer) mbar_wait(&sh.ybar, yphase);
+#ifdef FUSED_PROFILE
+        if (ct == 0) atomicAdd(&g_fused_cycles[FP_X2], (unsigned long long)(clock64() - xp0));
+#endif
+        yphase ^= 1;
+        tc_fence_before();
+        G::sync();
+        // ---- everyone: this thread's row of z
+        tc_fence_after();
+        read_product(z, dinv_s, fulln);
+        FPHASE_END(FP_PRODUCT);
+        if (test && misc[2] != 0.f) {
+          // |y_c - U h_c|_D^2 + coupling to the trailing columns, summed over the wanted columns: bounds the residual
+          // of every Ritz pair of the leading block.  Thread = token: r_c = y_c - sum_a u_a H[a][c]
+          // (columns c >= kk are not needed: with kk <= 8 only the first two 128-bit pieces of every H row are read)
+          float r[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) r[c] = y[c];
+          const int nq = (kk + 3) >> 2;   // 128-bit pieces of an H row that hold wanted columns
+#pragma unroll
+          for (int a = 0; a < 16; ++a) {
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              if (qq < nq) {   // uniform
+                const float4 h = *reinterpret_cast<const float4*>(Hs + a * ld + 4 * qq);
+                r[4 * qq] = fmaf(-u[a], h.x, r[4 * qq]);
+                r[4 * qq + 1] = fmaf(-u[a], h.y, r[4 * qq + 1]);
+                r[4 * qq + 2] = fmaf(-u[a], h.z, r[4 * qq + 2]);
+                r[4 * qq + 3] = fmaf(-u[a], h.w, r[4 * qq + 3]);
+              }
+            }
+          }
+          float tot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < kk && Hs[c * ld + c] >= P.lam_floor) tot = fmaf(d * r[c], r[c], tot);
+          if (ct < kk && Hs[ct * ld + ct] >= P.lam_floor)   // the coupling terms of column ct are added once
+            for (int a = kk; a < me; ++a) tot = fmaf(Hs[a * ld + ct], Hs[a * ld + ct], tot);
+          tot = warp_sum(tot);
+          if (lane == 0) red[cw] = tot;
+          G::sync();
+          float all = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < kCompute / 32; ++w8) all += red[w8];
+          fired = all <= tol2;
         }
         FPHASE_END(FP_TRIGGER);
         if (fired || last) break;
 
-        // ---- U = orth_D(Y): Cholesky of G2 on one warp, forward substitution per token
-        float piv = eig::cholesky_lt16<G>(Gs, m, me, LT, pinv, misc);
-        FPHASE_END(FP_CHOL);
-        eig::forward_subst16(y, LT, pinv, u);
-        if ((P.debug & 15) == 5) break;
-        if (piv < EIG_REORTH) {
-          // ill-conditioned block (early iterations): orthonormalise once more
-          G::sync();   // every thread has read LT / pinv
+        // ---- next iterate: u = L^-1 y (D-orthonormal), y = L^-1 z = D^-1 A u
+        float piv = misc[0];
+        {
+          float t[16];
+          eig::forward_subst16(y, LT, pinv, t);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) u[c] = t[c];
+          eig::forward_subst16(z, LT, pinv, t);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) y[c] = t[c];
+        }
+        if (piv < EIG_REORTH && !(P.debug & 1024)) {
+          // ill-conditioned block (early iterations): orthonormalise once more.  G3 = U^T D U from the operand rows
+          // [U_hi; U_lo] of block A against [DU_hi; DU_lo] in block B (the product that read block A has completed).
           if (row < npad) {
+            store_rows(opa_tok, 32, u, kUScale, true);
+            float du[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) Ut[c * ldt + row] = u[c];
+            for (int c = 0; c < 16; ++c) du[c] = d * u[c];
+            store_rows(opb_tok, 0, du, kDScale, true);
           }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          G::sync();   // also: every thread has read LT / pinv
+          if (cw == 1) issue_gram(32);
+          if (q == 0 && tile == 0) {
+            mbar_wait(&sh.gbar, gphase);
+            tc_fence_after();
+            float g3[16];
+            read_gram_rows(g3, 1.0f / (kUScale * kDScale));
+            float dorig = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dorig = lane == c ? g3[c] : dorig;
+            eig::cholesky_lt16_regs(g3, dorig, me, LT, pinv, misc, rowbuf);
+          }
+          gphase ^= 1;
+          tc_fence_before();
           G::sync();
-          eig::weighted_grams<G>(Ut, Ut, dg, n, m, ldt, kMB, Gs, Hs, false, gscr);
-          piv = eig::cholesky_lt16<G>(Gs, m, me, LT, pinv, misc);
-          float u2[16];
-          eig::forward_subst16(u, LT, pinv, u2);
+          float t[16];
+          eig::forward_subst16(u, LT, pinv, t);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) u[c] = u2[c];
-        }
-        if (row < npad) {
+          for (int c = 0; c < 16; ++c) u[c] = t[c];
+          eig::forward_subst16(y, LT, pinv, t);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) Ut[c * ldt + row] = u[c];
+          for (int c = 0; c < 16; ++c) y[c] = t[c];
         }
-        // (the barrier before the next product orders these writes before the next Gram step)
         FPHASE_END(FP_SUBST);
+        if ((P.debug & 15) == 6 && it == P.max_iter - 1) break;            // development: output u after `it` updates
+        if ((P.debug & 15) == 7 && it == P.max_iter - 1) {                 // ... or its image y
+#pragma unroll
+          for (int c = 0; c < 16; ++c) u[c] = y[c];
+          break;
+        }
+        // (the barrier after the next operand write orders the reads of LT / pinv before the next factorisation)
       }
 
       // ---- output: the basis, the projected operator, the verdict
@@ -510,7 +642,7 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
       }
       {
         const int a = ct >> 4, c = ct & 15;
-        P.H[static_cast<size_t>(s) * 256 + ct] = (a < m && c < m) ? Hs[a * ld + c] : 0.f;
+        P.H[static_cast<size_t>(s) * 256 + ct] = (a < m && c < m) ? ((P.debug & 512) ? LT : ((P.debug & 256) ? Gs : Hs))[a * ld + c] : 0.f;
       }
       if (ct == 0) {
         P.iters[s] = it;
@@ -520,7 +652,7 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.tmem_empty);
-      G::sync();   // rq / dg / Hs may be overwritten by the next segment
+      G::sync();   // rq / Hs may be overwritten by the next segment
       FPHASE_END(FP_OUTPUT);
     }
   }
@@ -590,7 +722,7 @@ extern "C" int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U
   }
 
   const size_t fixed = 1024 + kUopBytes + ((sizeof(Shared) + 15) & ~size_t(15)) +
-                       static_cast<size_t>(make_eig_layout(N).total) * sizeof(float);
+                       static_cast<size_t>(make_eig_layout().total) * sizeof(float);
   const size_t kMaxSmem = 227 * 1024;
   int stages = static_cast<int>((kMaxSmem - fixed) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

@@ -52,7 +52,7 @@ def run(argv):
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     print(f"fused kernel median {ts[len(ts)//2]:.4f} ms min {ts[0]:.4f}; iters mean {iters.float().mean():.2f} max {int(iters.max())} converged {int(info.sum())}/{B}")
-    names = ["gram", "epilogue", "init", "uop", "product", "drain", "grams", "trigger", "chol", "subst", "output"]
+    names = ["gram", "epilogue", "init", "uop", "product", "drain", "grams", "trigger", "chol", "subst", "output", "x1_cholesky_warp", "x2_ybar_wait"]
     buf = (ctypes.c_ulonglong * len(names))()
     lib.msvit_fused_profile(buf, 1)
     call(); torch.cuda.synchronize()
