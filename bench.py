@@ -65,24 +65,34 @@ def workload(name: str):
 
 
 def workload_string(name, B, N, D, K, k, dtype_name):
-    return (f"{name}: ViT-B/16 224px tokens [B={B} per GPU, N={N}, D={D}] {dtype_name}, rbf NCut affinity "
+    model = {"C1": "ViT-B/16 224px", "C2": "ViT-B/16 224px", "C3": "ViT-L/14 336px", "C4": "ViT-B/14 448px (1024 tokens)"}[name]
+    return (f"{name}: {model} tokens [B={B} per GPU, N={N}, D={D}] {dtype_name}, rbf NCut affinity "
             f"(gamma=3, scale=D/4), k={k} eigenvectors, K={K} k-means clusters, cluster-mean pooling")
 
 
 # ------------------------------------------------------------------------------------------ algorithmic work
-def stage_work(B, N, D, K, k, esz):
+def stage_work(B, N, D, K, k, esz, fused=False, block=16, eig_iters=0.0):
     """Algorithmic bytes / flops of ONE launch of each stage kernel over B images (DESIGN.md section 4;
     per-image figures are SURVEY.md section 8d's)."""
     lda = (N + 3) & ~3
     w = {}
-    # affinity: read X once, write A (fp32, padded rows) and deg; flops = Gram 2 N^2 D
-    w["affinity"] = {"bytes": B * (esz * N * D + 4 * N * lda + 4 * N), "flops": 2.0 * B * N * N * D}
-    # eigensolver: compulsory traffic = A and deg once, V and lambda out (A is re-read from L2 every iteration)
-    w["eig"] = {"bytes": B * (4 * N * lda + 4 * N + 4 * N * k + 4 * k), "flops": 0.0}
-    # k-means: read V, lambda, deg; write labels (int32) and the child count
-    w["kmeans"] = {"bytes": B * (4 * N * k + 4 * k + 4 * N + 4 * N + 4), "flops": 0.0}
-    # label composition: read int32 labels + counts, write int64 labels
-    w["compose"] = {"bytes": B * (4 * N + 4 + 8 * N), "flops": 0.0}
+    if fused:
+        # fused affinity + subspace iteration: read X once; out: degree, the basis U [N, 16] and H [16, 16].  The
+        # affinity never leaves tensor memory.  flops: Gram 2 N^2 D + (products 2 N^2 m + Grams 4 N m^2) per iteration
+        w["affinity"] = {"bytes": B * (esz * N * D + 4 * N + 4 * N * block + 4 * block * block),
+                         "flops": B * (2.0 * N * N * D + eig_iters * (2.0 * N * N * block + 4.0 * N * block * block))}
+        # Ritz rotation + k-means: read U, H, deg; write V, lambda, int64 labels, child count
+        w["kmeans"] = {"bytes": B * (4 * N * block + 4 * block * block + 4 * N + 4 * N * k + 4 * k + 8 * N + 4),
+                       "flops": 0.0}
+    else:
+        # affinity: read X once, write A (fp32, padded rows) and deg; flops = Gram 2 N^2 D
+        w["affinity"] = {"bytes": B * (esz * N * D + 4 * N * lda + 4 * N), "flops": 2.0 * B * N * N * D}
+        # eigensolver: compulsory traffic = A and deg once, V and lambda out (A is re-read from L2 every iteration)
+        w["eig"] = {"bytes": B * (4 * N * lda + 4 * N + 4 * N * k + 4 * k), "flops": 0.0}
+        # k-means: read V, lambda, deg; write labels (int32) and the child count
+        w["kmeans"] = {"bytes": B * (4 * N * k + 4 * k + 4 * N + 4 * N + 4), "flops": 0.0}
+        # label composition: read int32 labels + counts, write int64 labels
+        w["compose"] = {"bytes": B * (4 * N + 4 + 8 * N), "flops": 0.0}
     # pooling: read X and int64 labels, write pooled fp32 and counts
     w["pool"] = {"bytes": B * (esz * N * D + 8 * N + 4 * K * D + 4 * K), "flops": 0.0}
     return w
@@ -295,14 +305,17 @@ def run_ours(args):
         return
 
     peaks = load_peaks()
-    work = stage_work(B, N, D, K, k, esz)
+    work = stage_work(B, N, D, K, k, esz, fused=plan.fused, block=plan.block, eig_iters=eig_iters["mean"])
+    kernel_of = ({"affinity": "ncut_fused_kernel (affinity + subspace iteration, affinity kept in TMEM)",
+                  "kmeans": "ritz_kmeans_kernel (Rayleigh-Ritz + k-means + labels)", "pool": "pool_kernel"}
+                 if plan.fused else {n: n for n in ClusterPlan.STAGES})
     stages = {}
     for name in ClusterPlan.STAGES:
         ms = stage_ms[name]
         if name not in work or ms <= 0:
             continue
         w = work[name]
-        stages[name] = {"ms": round(ms, 4), "GB/s": round(w["bytes"] / ms / 1e6, 1)}
+        stages[name] = {"kernel": kernel_of.get(name, name), "ms": round(ms, 4), "GB/s": round(w["bytes"] / ms / 1e6, 1)}
         if w["flops"]:
             stages[name]["TFLOP/s"] = round(w["flops"] / ms / 1e9, 1)
     dominant = max(stages, key=lambda n: stages[n]["ms"])
@@ -310,19 +323,25 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.config, {}).get(dominant)
-    if dominant == "affinity":
+            tkey = {"affinity": "ncut_fused", "kmeans": "ritz_kmeans"}.get(dominant, dominant) if plan.fused else dominant
+            traffic = json.load(f).get(args.config, {}).get(tkey)
+    if dominant == "affinity" and not plan.fused:
         # the Gram contraction is the one tensor-core-bound kernel of the path
         ach = stages[dominant]["TFLOP/s"]
         peak = peaks["bf16_tflops_sustained"]
-        roof = {"kernel": dominant, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        roof = {"kernel": kernel_of[dominant], "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["_source"] + ", sustained bf16"}
     else:
         ach = stages[dominant]["GB/s"]
         peak = peaks["hbm_gbs"]
-        roof = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roof = {"kernel": kernel_of[dominant], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peaks["_source"]}
     roof["share_of_step"] = round(stages[dominant]["ms"] / sum(s["ms"] for s in stages.values()), 3)
+    if dominant == "affinity" and plan.fused:
+        roof["note"] = ("compulsory HBM traffic = the tokens once (the affinity stays in tensor memory); the kernel is bound by "
+                        "the per-image dependency chain of the subspace iteration (one image per SM at a time), "
+                        "see profiles/r2_summary.md")
+        roof["tensor_tflops"] = stages[dominant].get("TFLOP/s")
     if dominant == "eig":
         # the eigensolver is bound by per-segment dependency latency, not by a pipe (profiles/r1c_summary.md): its
         # HBM figure is the compulsory traffic (affinity once); its tensor-core products are reported next to it
@@ -342,8 +361,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.config, B, N, D, K, k, args.dtype),
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2_policy": f"inputs larger than L2 ({B * N * D * esz / 1e6:.0f} MB tokens + "
-                                f"{B * N * ((N + 3) & ~3) * 4 / 1e6:.0f} MB affinity per step vs 126 MB L2)",
+                   "l2_policy": f"inputs larger than L2 ({B * N * D * esz / 1e6:.0f} MB tokens per step vs 126 MB L2)",
+                   "path": "fused (affinity in tensor memory)" if plan.fused else "affinity + eig kernels (affinity through L2)",
                    "eig_iters": eig_iters},
         "roofline": roof, "stages": stages,
         "cpu_baseline": {"value": round(cpu_rate, 2), "unit": UNIT, "cores": cores, "kind": "port",
@@ -385,7 +404,7 @@ def run_c5(args):
     msvit._lib.load()
     n_total, D, k = args.c5_rows, 768, 1000
     first, n = shard_bounds(n_total, rank, world)
-    dtype = torch.bfloat16 if args.dtype != "float32" or True else torch.float32
+    dtype = torch.bfloat16   # the dataset-level path takes bf16 features
     # planted mixture: centres1000[label] + 0.5 randn, seed 1212; every rank generates its own rows
     g = torch.Generator(device=dev).manual_seed(1212)
     centres = torch.randn(k, D, generator=g, device=dev)

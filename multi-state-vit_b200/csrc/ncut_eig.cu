@@ -150,8 +150,11 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
             const float gcc = Gs[c * ld + c];
             float e = gcc;
             for (int a = 0; a < kk; ++a) e = fmaf(-Hs[a * ld + c], Hs[a * ld + c], e);
+            // exempt only if even the upper bound theta + |r| of the eigenvalue is below the floor (Ritz values
+            // approach it from below: an early estimate alone must not excuse a pair from converging)
+            const bool wanted = Hs[c * ld + c] + sqrtf(fmaxf(e, 0.f)) >= P.lam_floor;
             e -= 64.f * tol2 + 8e-6f * gcc;
-            if (Hs[c * ld + c] >= P.lam_floor) v = fmaxf(v, e);
+            if (wanted) v = fmaxf(v, e);
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
           for (int c = lane; c < kk; c += 32) {
             float v = res[c];
             for (int a = kk; a < me; ++a) v = fmaf(Hs[a * ld + c], Hs[a * ld + c], v);
-            if (Hs[c * ld + c] >= P.lam_floor) worst = fmaxf(worst, v);
+            if (Hs[c * ld + c] + sqrtf(fmaxf(v, 0.f)) >= P.lam_floor) worst = fmaxf(worst, v);
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(THREADS, (128 * EIG_MINB / THREADS) > 0 ? (128
         if (warp == 0) {
           float worst = 0.f;
           for (int c = lane; c < kk; c += 32)
-            if (theta[c] >= P.lam_floor) worst = fmaxf(worst, res[c]);
+            if (theta[c] + sqrtf(fmaxf(res[c], 0.f)) >= P.lam_floor) worst = fmaxf(worst, res[c]);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
           if (lane == 0) misc[1] = worst;

@@ -512,8 +512,10 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
             const float gcc = Gs[c * ld + c];
             float e = gcc;
             for (int a = 0; a < kk; ++a) e = fmaf(-Hs[a * ld + c], Hs[a * ld + c], e);
+            // exempt only if even the upper bound theta + |r| of the eigenvalue is below the floor
+            const bool wanted = Hs[c * ld + c] + sqrtf(fmaxf(e, 0.f)) >= P.lam_floor;
             e -= 64.f * tol2 + 8e-6f * gcc;
-            if (Hs[c * ld + c] >= P.lam_floor) v = fmaxf(v, e);
+            if (wanted) v = fmaxf(v, e);
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -559,19 +561,39 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
               }
             }
           }
-          float tot = 0.f;
+          if (P.lam_floor <= 0.f) {
+            float tot = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < kk && Hs[c * ld + c] >= P.lam_floor) tot = fmaf(d * r[c], r[c], tot);
-          if (ct < kk && Hs[ct * ld + ct] >= P.lam_floor)   // the coupling terms of column ct are added once
-            for (int a = kk; a < me; ++a) tot = fmaf(Hs[a * ld + ct], Hs[a * ld + ct], tot);
-          tot = warp_sum(tot);
-          if (lane == 0) red[cw] = tot;
-          G::sync();
-          float all = 0.f;
+            for (int c = 0; c < 16; ++c)
+              if (c < kk) tot = fmaf(d * r[c], r[c], tot);
+            if (ct < kk)   // the coupling terms of column ct are added once
+              for (int a = kk; a < me; ++a) tot = fmaf(Hs[a * ld + ct], Hs[a * ld + ct], tot);
+            tot = warp_sum(tot);
+            if (lane == 0) red[cw * 16] = tot;
+            G::sync();
+            float all = 0.f;
 #pragma unroll
-          for (int w8 = 0; w8 < kCompute / 32; ++w8) all += red[w8];
-          fired = all <= tol2;
+            for (int w8 = 0; w8 < kCompute / 32; ++w8) all += red[w8 * 16];
+            fired = all <= tol2;
+          } else {
+            // eigenvalue-threshold mode: a column whose eigenvalue cannot reach the floor (theta + |r| < floor) is
+            // exempt, which needs the residual column by column
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float e = warp_sum(c < kk ? d * r[c] * r[c] : 0.f);
+              if (lane == 0) red[cw * 16 + c] = e;
+            }
+            G::sync();
+            float all = 0.f;
+            for (int c = 0; c < kk; ++c) {
+              float e = 0.f;
+#pragma unroll
+              for (int w8 = 0; w8 < kCompute / 32; ++w8) e += red[w8 * 16 + c];
+              for (int a = kk; a < me; ++a) e = fmaf(Hs[a * ld + c], Hs[a * ld + c], e);
+              if (Hs[c * ld + c] + sqrtf(e) >= P.lam_floor) all += e;
+            }
+            fired = all <= tol2;
+          }
         }
         FPHASE_END(FP_TRIGGER);
         if (fired || last) break;

@@ -9,7 +9,9 @@ Differences from the reference that are deliberate:
     pooled over the whole batch (:83-84);
   * a parent with no eigenvalue above the threshold yields exactly one child AND advances the child offset
     (the reference adds 0 at :94, which would make two parents share an id);
-  * exact (tolerance-driven) eigenvectors and deterministic k-means seeding instead of randomised ones.
+  * exact (tolerance-driven) eigenvectors and deterministic k-means seeding instead of randomised ones;
+  * `cluster_size_threshold` is accepted and ignored: the reference only reads it in its plotting branch
+    (modeling_spectral.py:110-113).
 """
 from __future__ import annotations
 
@@ -28,7 +30,12 @@ class SpectralClusteringConfig(ClusteringConfig):
     ncut_dist: Literal["rbf", "cosine"] = None
     eigenvalue_threshold: float = None
     cluster_size_threshold: float = None
-    # ---- additions (defaults reproduce the reference's NCUT(...) arguments, modeling_spectral.py:54-61)
+    # ---- additions.  affinity_focal_gamma = 3.0 is the reference's NCUT(...) argument (modeling_spectral.py:59).
+    # distance_scale is OURS: the rbf distance is 1/2 |xi - xj|^2 / s with s = hidden size by default, so that gamma does
+    # not depend on the width of the model; s = 1.0 gives the raw form of sandbox/ncut_euclidean.py:19,23-29.  ncut-pytorch's
+    # own feature scaling cannot be inspected here (the package is absent), so an eigenvalue_threshold tuned against
+    # the reference's eigenvalues has to be re-tuned.  "normprod" (sandbox/test.py:108-110) is not a positive
+    # semi-definite kernel in general: the solver returns the pairs largest in magnitude.
     affinity_focal_gamma: float = 3.0
     distance_scale: Optional[float] = None   # None -> hidden size (rbf / normprod)
     n_clusters: Optional[int] = None         # fixed children per parent instead of the eigenvalue threshold
@@ -41,6 +48,7 @@ class SpectralClustering(ClusteringModule):
     def __init__(self, config: SpectralClusteringConfig):
         super().__init__()
         self.config = config
+        self.last_output: Optional[F.ClusterOutput] = None   # eigenpairs, iterations and the converged flags of the last call
 
     def cluster(self, parent_indices: Optional[torch.LongTensor], x: torch.Tensor, **kwargs: Any) -> F.ClusterOutput:
         c = self.config
@@ -59,4 +67,5 @@ class SpectralClustering(ClusteringModule):
         bsz, N = parent_indices.shape
         if x.shape[:2] != (bsz, N):
             raise ValueError("parent_indices and x disagree on (batch, tokens)")
-        return self.cluster(parent_indices, x, **kwargs).labels
+        self.last_output = self.cluster(parent_indices, x, **kwargs)
+        return self.last_output.labels

@@ -28,16 +28,18 @@ class ClusterOutput:
     n_child: torch.Tensor           # [B, P] int32 children per parent
     degree: torch.Tensor            # [B, N] fp32 NCut degree
     iters: torch.Tensor             # [B, P] int32 eigensolver iterations
+    converged: torch.Tensor         # [B, P] bool: the wanted eigenpairs met the residual tolerance before the iteration cap
     affinity: Optional[torch.Tensor] = None  # [B, N, N] fp32 (single-parent case with N % 4 == 0 only)
 
 
 FUSED_BLOCK = 16     # subspace width of the fused kernel
-FUSED_MAX_TOKENS = 224
+FUSED_MAX_TOKENS = 208
 
 
-def fused_eligible(N: int, block: int, n_parents: int = 1) -> bool:
-    """Shapes msvit_ncut_fused takes: whole images, 16 < N, round16(N) <= 224, subspace width 16."""
-    return n_parents == 1 and block == FUSED_BLOCK and FUSED_BLOCK < N and ((N + 15) & ~15) <= FUSED_MAX_TOKENS
+def fused_eligible(N: int, k: int, n_parents: int = 1) -> bool:
+    """Shapes msvit_ncut_fused takes: whole images, 16 < N, round16(N) <= 208, ncut_dim <= 12 (the fused kernel always
+    iterates on a block of 16 columns, i.e. at least 4 columns of oversampling)."""
+    return n_parents == 1 and k + 4 <= FUSED_BLOCK and FUSED_BLOCK < N and ((N + 15) & ~15) <= FUSED_MAX_TOKENS
 
 
 def default_block(k: int, oversample: int = 8) -> int:
@@ -85,8 +87,9 @@ class ClusterPlan:
         self.scale = float(D) if scale is None else float(scale)
         self.nk = int(n_clusters) if n_clusters is not None else 0
         self.thr = float(eigenvalue_threshold) if eigenvalue_threshold is not None else 0.0
-        # eigenpairs below half the threshold are never clustered on: exempt them from the residual test
-        self.lam_floor = 0.5 * self.thr if self.nk == 0 else 0.0
+        # eigenpairs that cannot reach the threshold (Ritz value + residual norm < threshold) are never clustered on:
+        # they are exempt from the residual test
+        self.lam_floor = self.thr if self.nk == 0 else 0.0
         # with a fixed number of clusters K < k the k-means step reads V[:, :K] only: the other pairs need not converge
         self.n_converge = min(self.nk, self.k) if self.nk > 0 else 0
         self.kmeans_iters, self.eig_iters, self.eig_tol = int(kmeans_iters), int(eig_iters), float(eig_tol)
@@ -95,11 +98,12 @@ class ClusterPlan:
         B, N, D, P, k = self.B, self.N, self.D, self.P, self.k
         self.S = B * P
         # whole images of up to 224 tokens take the fused kernel: the affinity stays in tensor memory
-        can_fuse = fused_eligible(N, self.block, P)
+        can_fuse = fused_eligible(N, self.k, P)
         if fused and not can_fuse:
-            raise ValueError("the fused kernel needs whole images (one parent), 16 < tokens <= 224 and a subspace "
-                             "width of 16 (ncut_dim <= 8 with the default oversampling)")
+            raise ValueError("the fused kernel needs whole images (one parent), 16 < tokens <= 208 and ncut_dim <= 12")
         self.fused = can_fuse if fused is None else bool(fused)
+        if self.fused:
+            self.block = FUSED_BLOCK
         rows = B * N
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -152,6 +156,9 @@ class ClusterPlan:
             if P > 1:
                 if parent_indices.shape != (B, N) or parent_indices.dtype != torch.int64:
                     raise ValueError("parent_indices must be int64 [batch, tokens]")
+                if parent_indices.device != self.device:
+                    raise ValueError(f"parent_indices must live on {self.device} (got {parent_indices.device}); the kernels "
+                                     "take raw device pointers")
                 parent_indices = parent_indices.contiguous()
                 check(lib.msvit_build_segments(p(parent_indices), p(self.perm), p(self.seg_off), p(self.a_off), B, N, P,
                                                st), "msvit_build_segments")
@@ -202,9 +209,12 @@ class ClusterPlan:
         else:
             V_tok, deg_tok = self.V, self.deg
         aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0 and not self.fused) else None
+        # the fused kernel reports its verdict; the two-kernel solver stops at the cap only when it did not converge
+        conv = (self.info == 1) if self.fused else (self.iters < self.eig_iters)
         return ClusterOutput(labels=self.child, pooled=self.pooled, counts=self.counts, eigvecs=V_tok.view(B, N, k),
                              eigvals=self.lam.view(B, P, k), n_child=self.n_child.view(B, P),
-                             degree=deg_tok.view(B, N), iters=self.iters.view(B, P), affinity=aff)
+                             degree=deg_tok.view(B, N), iters=self.iters.view(B, P), converged=conv.view(B, P),
+                             affinity=aff)
 
 
 def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, *, ncut_dim: int,
@@ -224,6 +234,10 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
     else:
         if tuple(parent_indices.shape) != (B, N):
             raise ValueError("parent_indices must be [batch, tokens]")
+        if parent_indices.dtype != torch.int64:
+            raise ValueError(f"parent_indices must be int64 (got {parent_indices.dtype})")
+        if parent_indices.device != x.device:
+            parent_indices = parent_indices.to(x.device)   # e.g. the caller's initial all-zero indices built on the host
         # the reference reads this on the host too (modeling_spectral.py:80); pass n_parents to skip the sync
         P = int(n_parents) if n_parents is not None else int(parent_indices.max().item()) + 1
         if P == 1:
@@ -315,6 +329,10 @@ def cluster_attention_stats(attention_probs: torch.Tensor, cluster_indices: torc
     if attention_probs.dtype != torch.float32:
         raise TypeError("attention_probs must be float32")
     B, H, N, _ = attention_probs.shape
+    if tuple(cluster_indices.shape) != (B, N) or cluster_indices.dtype != torch.int64:
+        raise ValueError("cluster_indices must be int64 [batch, tokens]")
+    if cluster_indices.device != attention_probs.device:
+        raise ValueError("cluster_indices must live on the same device as attention_probs")
     C = int(n_clusters)
     a = attention_probs.contiguous()
     lab = cluster_indices.contiguous()

@@ -1,0 +1,170 @@
+"""GPU tests (`-m gpu`) of the fused affinity + NCut kernel (msvit_ncut_fused + msvit_ritz_kmeans) and of the
+properties the round-1 review asked for: agreement of the fused and the two-kernel paths, the error against the
+UN-ROUNDED fp32 oracle, degenerate (non-planted) spectra with the converged flag, CUDA-graph replay.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ncut_oracle as O  # noqa: E402
+import msvit  # noqa: E402
+from msvit import functional as F  # noqa: E402
+from msvit.functional import ClusterPlan  # noqa: E402
+from msvit.synthetic import default_scale, planted_tokens  # noqa: E402
+
+DEV = "cuda:0"
+RTOL = 1e-3
+
+
+def seen(x, dtype):
+    return O.round_to_bf16(x) if dtype == torch.bfloat16 else O.round_to_tf32(x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(8, 196, 768, 8), (5, 100, 64, 4), (3, 208, 128, 6), (4, 33, 32, 3), (2, 128, 96, 5)])
+def test_fused_path_matches_two_kernel_path_and_oracle(dtype, shape):
+    B, N, D, K = shape
+    assert F.fused_eligible(N, K)
+    x, _ = planted_tokens(B, N, D, K)
+    xd = x.to(dtype).to(DEV)
+    kw = dict(ncut_dim=K, n_clusters=K, scale=default_scale(D))
+    fused = ClusterPlan(B, N, D, dtype, DEV, fused=True, **kw).run(xd)
+    plain = ClusterPlan(B, N, D, dtype, DEV, fused=False, **kw).run(xd)
+    torch.cuda.synchronize()
+    assert bool(fused.converged.all()) and bool(plain.converged.all())
+    assert torch.equal(fused.labels, plain.labels)
+    assert torch.equal(fused.counts, plain.counts)
+    torch.testing.assert_close(fused.degree, plain.degree, rtol=1e-5, atol=0)
+    torch.testing.assert_close(fused.eigvals[:, 0, :K], plain.eigvals[:, 0, :K], rtol=1e-4, atol=1e-6)
+    child, _, eigvals, _ = O.cluster_tokens(seen(x, dtype).double(), None, ncut_dim=K, n_clusters=K, scale=default_scale(D))
+    assert torch.equal(fused.labels.cpu(), child)
+    np.testing.assert_allclose(fused.eigvals[:, 0, :K].cpu().numpy(), eigvals[:, 0, :K].numpy(), rtol=RTOL, atol=1e-6)
+    for b in range(min(B, 3)):
+        A = O.affinity(seen(x, dtype)[b].double(), "rbf", 3.0, default_scale(D))
+        Vref, lref, dref = O.ncut_eig(A, K + 4)
+        np.testing.assert_allclose(fused.degree[b].cpu().numpy(), dref.numpy(), rtol=RTOL)
+        V = fused.eigvecs[b].cpu().double()
+        for j in range(K):
+            gap = min(abs(lref[j] - lref[i]) for i in range(K + 4) if i != j)
+            err = float(torch.linalg.norm(V[:, j] - Vref[:, j]))
+            assert err <= 1e-3 + 2e-4 / max(float(gap), 1e-9), f"eigvec {j}: err {err:.2e} gap {float(gap):.2e}"
+            assert V[torch.argmax(V[:, j].abs()), j] > 0       # canonical sign
+
+
+def test_fused_threshold_mode_and_module_forward():
+    B, N, D, K = 4, 196, 768, 8
+    x, _ = planted_tokens(B, N, D, K)
+    out = msvit.cluster_tokens(x.to(DEV), ncut_dim=K, eigenvalue_threshold=0.05, scale=default_scale(D), fused=True)
+    child, _, _, nc = O.cluster_tokens(O.round_to_tf32(x).double(), None, ncut_dim=K, eigenvalue_threshold=0.05,
+                                       scale=default_scale(D))
+    assert out.n_child.cpu().tolist() == nc.tolist()
+    assert torch.equal(out.labels.cpu(), child)
+    # threshold above every non-trivial eigenvalue: one child per image
+    one = msvit.cluster_tokens(x.to(DEV), ncut_dim=K, eigenvalue_threshold=0.9, scale=default_scale(D), fused=True)
+    assert one.n_child.cpu().flatten().tolist() == [1] * B and int(one.labels.max()) == 0
+
+
+def test_c1_error_against_the_unrounded_fp32_oracle():
+    """BASELINE.json configs[0] (B=8): the whole path on fp32 tokens against the oracle fed the SAME un-rounded fp32
+    tokens (the tensor cores read them as TF32, so this includes the operand rounding): the stated bar is 1e-3."""
+    B, N, D, K = 8, 196, 768, 8
+    x, _ = planted_tokens(B, N, D, K)
+    xd = x.to(DEV)
+    fused = msvit.cluster_tokens(xd, ncut_dim=K, n_clusters=K, scale=default_scale(D), fused=True)
+    plain = msvit.cluster_tokens(xd, ncut_dim=K, n_clusters=K, scale=default_scale(D), fused=False, keep_affinity=True)
+    child, _, eigvals, _ = O.cluster_tokens(x.double(), None, ncut_dim=K, n_clusters=K, scale=default_scale(D))
+    pooled_ref, _ = O.pool(x.double(), child, K)
+    worst = {"affinity": 0.0, "degree": 0.0}
+    for b in range(B):
+        A = O.affinity(x[b].double(), "rbf", 3.0, default_scale(D))
+        worst["affinity"] = max(worst["affinity"], float(((plain.affinity[b].cpu().double() - A).abs() / A).max()))
+        worst["degree"] = max(worst["degree"], float(((fused.degree[b].cpu().double() - A.sum(-1)).abs() / A.sum(-1)).max()))
+    worst["eigenvalues"] = float(((fused.eigvals[:, 0].cpu().double() - eigvals[:, 0]).abs() / eigvals[:, 0].abs()).max())
+    worst["pooled"] = float(((fused.pooled.cpu().double() - pooled_ref).abs() / (pooled_ref.abs() + 1e-3)).max())
+    print("max relative error against the un-rounded fp32 oracle at C1:", {k: f"{v:.2e}" for k, v in worst.items()})
+    assert torch.equal(fused.labels.cpu(), child) and torch.equal(plain.labels.cpu(), child)
+    assert all(v < RTOL for v in worst.values()), worst
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_degenerate_spectrum_iid_tokens(fused):
+    """iid Gaussian tokens: lambda ~ [1, small, small, ...] with a slowly decaying noise bulk.
+    Eigenvectors are numerically arbitrary, but eigenvalues are not: they must match exact eigh to 1e-3, nothing may
+    be NaN, and a segment that stops at the iteration cap must say so through `converged`."""
+    B, N, D, k = 4, 196, 768, 8
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, N, D, generator=g)
+    out = msvit.cluster_tokens(x.to(DEV), ncut_dim=k, n_clusters=4, scale=default_scale(D), fused=fused, eig_iters=200)
+    assert torch.isfinite(out.eigvecs).all() and torch.isfinite(out.eigvals).all()
+    assert out.converged.dtype == torch.bool and out.converged.shape == (B, 1)
+    for b in range(B):
+        A = O.affinity(O.round_to_tf32(x[b]).double(), "rbf", 3.0, default_scale(D))
+        _, lref, _ = O.ncut_eig(A, k)
+        if bool(out.converged[b, 0]):
+            np.testing.assert_allclose(out.eigvals[b, 0, :4].cpu().numpy(), lref[:4].numpy(), rtol=RTOL, atol=1e-6)
+    # with a small cap the solver must report the segments it did not finish
+    capped = msvit.cluster_tokens(x.to(DEV), ncut_dim=k, n_clusters=k, scale=default_scale(D), fused=fused, eig_iters=3)
+    assert not bool(capped.converged.any())
+    assert torch.isfinite(capped.eigvecs).all()
+    assert int(capped.iters.max()) == 3
+
+
+def test_noisy_mixture_slow_spectrum_threshold_mode():
+    """A planted mixture drowned in noise (sigma = 2): eigenvalues decay slowly and the threshold cuts inside the bulk.
+    The number of children must equal the oracle's count of eigenvalues above the threshold (the exemption of pairs
+    below the threshold must not undercount)."""
+    B, N, D, k = 4, 196, 256, 8
+    x, _ = planted_tokens(B, N, D, 6, noise=2.0)
+    s = default_scale(D)
+    for fused in (True, False):
+        out = msvit.cluster_tokens(x.to(DEV), ncut_dim=k, eigenvalue_threshold=0.02, scale=s, fused=fused, eig_iters=300)
+        for b in range(B):
+            A = O.affinity(O.round_to_tf32(x[b]).double(), "rbf", 3.0, s)
+            _, lref, _ = O.ncut_eig(A, k)
+            margin = float((lref - 0.02).abs().min())
+            if margin > 2e-3 and bool(out.converged[b, 0]):      # the count is only defined away from the threshold
+                assert int(out.n_child[b, 0]) == max(1, int((lref > 0.02).sum())), (fused, b, lref.tolist())
+
+
+def test_plan_replays_in_a_cuda_graph_and_c1_latency():
+    """ClusterPlan.run allocates nothing and never synchronises: it can be captured once and replayed.
+    Reports the C1 (B=8) latency with and without the graph."""
+    B, N, D, K = 8, 196, 768, 8
+    x, _ = planted_tokens(B, N, D, K)
+    xd = x.to(DEV)
+    plan = ClusterPlan(B, N, D, torch.float32, DEV, ncut_dim=K, n_clusters=K, scale=default_scale(D))
+    ref = plan.run(xd)
+    torch.cuda.synchronize()
+    labels_ref, pooled_ref = ref.labels.clone(), ref.pooled.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan.run(xd)          # warm-up on the capture stream
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            plan.run(xd)
+    torch.cuda.current_stream().wait_stream(side)
+    plan.labels_view = None
+    ref.labels.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.child, labels_ref) and torch.equal(plan.pooled, pooled_ref)
+
+    def timed(fn, reps=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    eager = timed(lambda: plan.run(xd))
+    replay = timed(graph.replay)
+    print(f"C1 (B=8) latency: eager launches {eager * 1e3:.1f} us, CUDA-graph replay {replay * 1e3:.1f} us")
+    assert replay <= eager * 1.5
