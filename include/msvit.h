@@ -43,6 +43,9 @@ extern "C" {
 #define MSVIT_DIST_COSINE 1    /* d = 1 - cos(xi,xj)              model/clustering/modeling_spectral.py:62-69 */
 #define MSVIT_DIST_NORMPROD 2  /* d = (|xi||xj| - xi.xj) / scale  sandbox/test.py:108-110 */
 
+#define MSVIT_DISC_KMEANS 0      /* Lloyd k-means on the embedding      model/clustering/modeling_spectral.py:90 */
+#define MSVIT_DISC_AXIS_ALIGN 1  /* axis-aligned rotation (kway_ncut)   model/clustering/modeling_spectral.py:136-138 */
+
 #define MSVIT_MAX_EIG_BLOCK 32 /* subspace block (ncut_dim + oversampling) upper bound */
 
 typedef void* msvit_stream_t; /* cudaStream_t */
@@ -96,11 +99,11 @@ int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U, float* H,
 /* Rayleigh-Ritz finish of msvit_ncut_fused + the k-means of msvit_kmeans in one kernel (uniform segments):
  * V [S*N, k] eigenvectors (eigenvalues descending, sign canonical), lam [S, k]; then Lloyd k-means on V[:, :K] with
  * K = n_clusters > 0 ? n_clusters : max(1, #{lam > eig_threshold}) (modeling_spectral.py:87-93), seeded from the
- * row of largest degree.  labels [S*N] int32 and / or child [S*N] int64 (canonical ids; either may be NULL),
- * n_child [S]. */
+ * row of largest degree (method = MSVIT_DISC_KMEANS) or the axis-aligned rotation (MSVIT_DISC_AXIS_ALIGN).
+ * labels [S*N] int32 and / or child [S*N] int64 (canonical ids; either may be NULL), n_child [S]. */
 int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* info, const float* deg, float* V, float* lam,
                       int32_t* labels, int64_t* child, int32_t* n_child, int64_t total_rows, int S, int N, int k,
-                      int block, int n_converge, int n_clusters, float eig_threshold, int max_iter,
+                      int block, int n_converge, int n_clusters, float eig_threshold, int max_iter, int method,
                       msvit_stream_t stream);
 
 /* Lloyd k-means on the leading columns of the spectral embedding, per segment.
@@ -116,6 +119,14 @@ int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* info, const
 int msvit_kmeans(const float* V, const float* lam, const float* weight, const float* init, int32_t* labels,
                  int32_t* n_child, float* centres, int64_t total_rows, int S, int N, int ldv, int n_clusters,
                  float eig_threshold, int max_iter, const int32_t* seg_off, msvit_stream_t stream);
+
+/* Same interface with the discretisation method as an argument: MSVIT_DISC_KMEANS (= msvit_kmeans) or
+ * MSVIT_DISC_AXIS_ALIGN, the axis-aligned rotation of the embedding followed by argmax
+ * (replaces ncut_pytorch.kway_ncut, call sites modeling_spectral.py:136-138, modeling_axisalign.py:35-36; Yu & Shi
+ * 2003; at most 16 columns, no `init` / `centres`). */
+int msvit_discretise(const float* V, const float* lam, const float* weight, const float* init, int32_t* labels,
+                     int32_t* n_child, float* centres, int64_t total_rows, int S, int N, int ldv, int n_clusters,
+                     float eig_threshold, int max_iter, int method, const int32_t* seg_off, msvit_stream_t stream);
 
 /* Cluster-mean pooling of tokens into multi-state tokens.
  * Replaces the per-label mean loops (modeling_spectral.py:125-127, :271-273).

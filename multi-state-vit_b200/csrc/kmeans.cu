@@ -37,6 +37,7 @@ struct Params {
   float* lam_out;        // [S, ldv]
   int64_t* child;        // [rows] int64 labels (single parent: child id = canonical cluster id), may be NULL
   int m, kconv;
+  int discretise;        // 0 = k-means, 1 = axis-aligned rotation (kway_ncut)
 };
 
 // block-wide argmax of (value, index) with ties -> lowest index; result broadcast to all threads
@@ -209,6 +210,160 @@ __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, i
   }
 }
 
+// Scratch of the axis-aligned discretisation (K <= 16): small dense matrices with row stride 17.
+struct KwayScratch {
+  float* T;      // [16 * 17]  M^T M, then its eigenvalues on the diagonal
+  float* S;      // [16 * 17]  eigenvectors of M^T M
+  float* W;      // [16 * 17]  (M^T M)^-1/2
+  float* rot;    // [32]       Jacobi rotations (16-byte aligned)
+};
+constexpr int kKwayMaxK = 16;
+
+// Axis-aligned discretisation of the spectral embedding (Yu & Shi, "Multiclass spectral clustering", ICCV 2003 -- the
+// algorithm behind ncut_pytorch.kway_ncut; call sites model/clustering/modeling_spectral.py:136-138,
+// model/clustering/modeling_axisalign.py:35-36).  The package is absent from the reference checkout: the published
+// algorithm is restated (oracle/ncut_oracle.py:kway_ncut), parity is against that restatement (UNPINNED).
+//   Xn = rows of V[:, :K] scaled to unit length;   R = K rows of Xn chosen greedily as orthogonal as possible;
+//   repeat: labels = argmax_j (Xn R)_ij;  M = onehot(labels)^T Xn;  R = polar factor V U^T of M = U S V^T
+//   (computed as (M^T M)^-1/2 M^T with a Jacobi eigen-decomposition of the K x K matrix M^T M)
+// until the labels stop changing.  Same canonical relabelling and outputs as k-means.  w.pts holds V^T on entry.
+__device__ __forceinline__ void kway_segment(const Params& P, const Work& w, const KwayScratch& ks, int s, int row0, int n,
+                                             int K) {
+  using G = ThreadGroup<0, kThreads, 0>;
+  float* R = w.cen;           // [K][LDC]: R[d][j]
+  float* cacc = w.mind;       // [n]
+  int* lab = w.lab;
+  int* map = w.map;
+  float* part = w.part;       // [2][kMaxK * kMaxK]
+  int* pcnt = w.pcnt;
+  float* pts = w.pts;
+  const int ldp = w.ldp;
+  constexpr int LD = kKwayMaxK + 1;
+  int& s_changed = *w.changed;
+  // unit rows
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    float ss = 0.f;
+    for (int d = 0; d < K; ++d) ss = fmaf(pts[d * ldp + i], pts[d * ldp + i], ss);
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    for (int d = 0; d < K; ++d) pts[d * ldp + i] *= inv;
+    cacc[i] = 0.f;
+  }
+  // first column of R: the row of largest weight (degree), as the k-means seeding
+  int first = 0;
+  if (P.weight) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      const float wt = P.weight[row0 + i];
+      if (wt > bv) { bv = wt; bi = i; }
+    }
+    first = block_argmax(bv, bi, w.sval, w.sidx);
+    if (first < 0 || first >= n) first = 0;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < K; d += kThreads) R[d * LDC + 0] = pts[d * ldp + first];
+  __syncthreads();
+  for (int j = 1; j < K; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      float dot = 0.f;
+      for (int d = 0; d < K; ++d) dot = fmaf(pts[d * ldp + i], R[d * LDC + j - 1], dot);
+      const float c = cacc[i] + fabsf(dot);
+      cacc[i] = c;
+      if (-c > bv) { bv = -c; bi = i; }       // argmin c, ties -> lowest index
+    }
+    const int nxt = block_argmax(bv, bi, w.sval, w.sidx);
+    for (int d = threadIdx.x; d < K; d += kThreads) R[d * LDC + j] = pts[d * ldp + nxt];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += kThreads) lab[i] = -1;
+  __syncthreads();
+  const int Kp = (K + 1) & ~1;   // the Jacobi routine wants an even size: an odd K gets a decoupled unit pad
+  for (int it = 0; it < P.max_iter; ++it) {
+    if (threadIdx.x == 0) s_changed = 0;
+    __syncthreads();
+    int changed = 0;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      float best = -INFINITY;
+      int bj = 0;
+      for (int j = 0; j < K; ++j) {
+        float y = 0.f;
+        for (int d = 0; d < K; ++d) y = fmaf(pts[d * ldp + i], R[d * LDC + j], y);
+        if (y > best) { best = y; bj = j; }    // ties -> lowest j
+      }
+      if (lab[i] != bj) { lab[i] = bj; changed = 1; }
+    }
+    if (changed) s_changed = 1;
+    __syncthreads();
+    if (!s_changed) break;
+    // M[j][d] = sum of Xn[i][d] over the members of cluster j: two halves of the tokens in ascending order, fixed combine
+    const int nh = (n + 1) >> 1;
+    for (int e = threadIdx.x; e < 2 * K * K; e += kThreads) {
+      const int h = e / (K * K), r = e - h * K * K;
+      const int j = r / K, d = r - j * K;
+      const int i0 = h * nh, i1 = min(n, i0 + nh);
+      const float* pd = pts + d * ldp;
+      float sum = 0.f;
+      for (int i = i0; i < i1; ++i)
+        if (lab[i] == j) sum += pd[i];
+      part[h * kMaxK * kMaxK + r] = sum;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < K * K; r += kThreads) part[r] += part[kMaxK * kMaxK + r];   // M[j][d] at part[j * K + d]
+    __syncthreads();
+    // T = M^T M (symmetric, K x K), padded to Kp with a unit diagonal
+    for (int e = threadIdx.x; e < Kp * Kp; e += kThreads) {
+      const int a = e / Kp, b = e - a * Kp;
+      float t = 0.f;
+      if (a < K && b < K) {
+        for (int j = 0; j < K; ++j) t = fmaf(part[j * K + a], part[j * K + b], t);
+      } else {
+        t = a == b ? 1.f : 0.f;
+      }
+      ks.T[a * LD + b] = t;
+    }
+    __syncthreads();
+    eig::jacobi<G>(ks.T, ks.S, LD, Kp, 12, ks.rot);
+    // W = V diag(1 / sqrt(s2)) V^T
+    float smax = 0.f;
+    for (int a = 0; a < K; ++a) smax = fmaxf(smax, ks.T[a * LD + a]);
+    for (int e = threadIdx.x; e < K * K; e += kThreads) {
+      const int a = e / K, b = e - a * K;
+      float t = 0.f;
+      for (int c = 0; c < K; ++c) {
+        const float s2 = fmaxf(ks.T[c * LD + c], 1e-12f * smax);
+        t = fmaf(ks.S[a * LD + c] * rsqrtf(s2), ks.S[b * LD + c], t);
+      }
+      ks.W[a * LD + b] = t;
+    }
+    __syncthreads();
+    // R = W M^T:  R[d][j] = sum_e W[d][e] M[j][e]
+    for (int e = threadIdx.x; e < K * K; e += kThreads) {
+      const int d = e / K, j = e - d * K;
+      float t = 0.f;
+      for (int c = 0; c < K; ++c) t = fmaf(ks.W[d * LD + c], part[j * K + c], t);
+      R[d * LDC + j] = t;
+    }
+    __syncthreads();
+  }
+  // ---- canonical ids: clusters renamed in order of first occurrence
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < K; ++c) map[c] = -1;
+    int next = 0;
+    for (int i = 0; i < n && next < K; ++i)
+      if (map[lab[i]] < 0) map[lab[i]] = next++;
+    P.n_child[s] = next;
+  }
+  __syncthreads();
+  if (P.labels)
+    for (int i = threadIdx.x; i < n; i += kThreads) P.labels[row0 + i] = map[lab[i]];
+  if (P.child)
+    for (int i = threadIdx.x; i < n; i += kThreads) P.child[row0 + i] = map[lab[i]];
+  (void)pcnt;
+  __syncthreads();
+}
+
 __device__ __forceinline__ int select_k(const Params& P, const float* __restrict__ lam, int n) {
   int K;
   if (P.n_clusters > 0) {
@@ -226,6 +381,9 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
   __shared__ float sval[kThreads / 32];
   __shared__ int sidx[kThreads / 32];
   __shared__ int s_changed;
+  __shared__ float kT[16 * 17], kS[16 * 17], kW[16 * 17];
+  __shared__ __align__(16) float krot[32];
+  const KwayScratch ks{kT, kS, kW, krot};
   const Work w = carve(smem, P.N, sval, sidx, &s_changed);
 
   for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
@@ -244,7 +402,8 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
       if (j < K) w.pts[j * w.ldp + i] = Pt[e];
     }
     __syncthreads();
-    kmeans_segment(P, w, s, row0, n, K);
+    if (P.discretise == 1) kway_segment(P, w, ks, s, row0, n, K);
+    else kmeans_segment(P, w, s, row0, n, K);
   }
 }
 
@@ -351,7 +510,12 @@ __global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
     }
     __syncthreads();
     const int K = select_k(P, lam_s, n);
-    kmeans_segment(P, w, s, row0, n, K);
+    if (P.discretise == 1) {
+      const KwayScratch ks{Hm, Sm, Wm, rot};   // the Ritz step is done with them
+      kway_segment(P, w, ks, s, row0, n, K);
+    } else {
+      kmeans_segment(P, w, s, row0, n, K);
+    }
   }
 }
 
@@ -362,15 +526,27 @@ extern "C" int msvit_kmeans(const float* V, const float* lam, const float* weigh
                             int32_t* labels, int32_t* n_child, float* centres, int64_t total_rows, int S, int N,
                             int ldv, int n_clusters, float eig_threshold, int max_iter, const int32_t* seg_off,
                             msvit_stream_t stream_) {
+  return msvit_discretise(V, lam, weight, init, labels, n_child, centres, total_rows, S, N, ldv, n_clusters, eig_threshold,
+                          max_iter, MSVIT_DISC_KMEANS, seg_off, stream_);
+}
+
+extern "C" int msvit_discretise(const float* V, const float* lam, const float* weight, const float* init,
+                                int32_t* labels, int32_t* n_child, float* centres, int64_t total_rows, int S, int N,
+                                int ldv, int n_clusters, float eig_threshold, int max_iter, int method,
+                                const int32_t* seg_off, msvit_stream_t stream_) {
   using namespace msvit;
   using namespace msvit::km;
   if (!V || !labels || !n_child) return MSVIT_ERR_NULL;
   if (n_clusters <= 0 && !lam) return MSVIT_ERR_NULL;
   if (S < 0 || N <= 0 || ldv <= 0 || total_rows < 0 || max_iter <= 0) return MSVIT_ERR_SHAPE;
   if (n_clusters > kMaxK || n_clusters > ldv || (n_clusters <= 0 && ldv > kMaxK)) return MSVIT_ERR_SHAPE;
+  if (method != MSVIT_DISC_KMEANS && method != MSVIT_DISC_AXIS_ALIGN) return MSVIT_ERR_MODE;
+  if (method == MSVIT_DISC_AXIS_ALIGN && (n_clusters > kKwayMaxK || (n_clusters <= 0 && ldv > kKwayMaxK) || init || centres))
+    return MSVIT_ERR_SHAPE;
   if (!seg_off && total_rows != static_cast<int64_t>(S) * N) return MSVIT_ERR_SHAPE;
   if (S == 0 || total_rows == 0) return MSVIT_OK;
   Params P;
+  P.discretise = method;
   P.V = V; P.lam = lam; P.weight = weight; P.init = init; P.labels = labels; P.n_child = n_child;
   P.centres = centres; P.seg_off = seg_off;
   P.S = S; P.N = N; P.ldv = ldv; P.n_clusters = n_clusters; P.Kmax = n_clusters > 0 ? n_clusters : ldv;
@@ -391,7 +567,7 @@ extern "C" int msvit_kmeans(const float* V, const float* lam, const float* weigh
 extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* info, const float* deg, float* V,
                                  float* lam, int32_t* labels, int64_t* child, int32_t* n_child, int64_t total_rows,
                                  int S, int N, int k, int block, int n_converge, int n_clusters, float eig_threshold,
-                                 int max_iter, msvit_stream_t stream_) {
+                                 int max_iter, int method, msvit_stream_t stream_) {
   using namespace msvit;
   using namespace msvit::km;
   if (!U || !H || !info || !deg || !V || !lam || !n_child) return MSVIT_ERR_NULL;
@@ -399,6 +575,7 @@ extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* 
   if (S < 0 || N <= 0 || k <= 0 || total_rows < 0 || max_iter <= 0) return MSVIT_ERR_SHAPE;
   if (block != 16 || k > block || N <= block || n_converge < 0 || n_converge > block) return MSVIT_ERR_SHAPE;
   if (n_clusters > k) return MSVIT_ERR_SHAPE;
+  if (method != MSVIT_DISC_KMEANS && method != MSVIT_DISC_AXIS_ALIGN) return MSVIT_ERR_MODE;
   if (total_rows != static_cast<int64_t>(S) * N) return MSVIT_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(U) & 15) != 0) return MSVIT_ERR_ALIGN;
   if (S == 0) return MSVIT_OK;
@@ -409,6 +586,7 @@ extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* 
   P.max_iter = max_iter; P.thr = eig_threshold;
   P.U = U; P.H = H; P.info = info; P.Vout = V; P.lam_out = lam; P.child = child;
   P.m = block; P.kconv = n_converge > 0 ? n_converge : k;
+  P.discretise = method;
   const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N + 2 * kMaxK * kMaxK + static_cast<size_t>(k) * (N | 1)) +
                       sizeof(int) * (N + kMaxK + 2 * kMaxK);
   if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;

@@ -17,6 +17,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "msvit
 
 F32, BF16 = 0, 1
 DIST = {"rbf": 0, "cosine": 1, "normprod": 2}
+DISC = {"kmeans": 0, "axis_align": 1}
 MAX_EIG_BLOCK = 32
 
 _lock = threading.Lock()
@@ -34,7 +35,9 @@ _SIGNATURES = {
     "msvit_ncut_fused": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int,
                                   _c_int, _c_f32, _c_f32, _c_int, _c_int, _c_f32, _c_f32, _c_int, _c_ptr]),
     "msvit_ritz_kmeans": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int,
-                                   _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_ptr]),
+                                   _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _c_int, _c_ptr]),
+    "msvit_discretise": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int,
+                                  _c_int, _c_f32, _c_int, _c_int, _c_ptr, _c_ptr]),
     "msvit_kmeans": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_int,
                               _c_int, _c_f32, _c_int, _c_ptr, _c_ptr]),
     "msvit_pool": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr]),

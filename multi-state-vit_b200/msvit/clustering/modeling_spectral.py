@@ -39,6 +39,7 @@ class SpectralClusteringConfig(ClusteringConfig):
     affinity_focal_gamma: float = 3.0
     distance_scale: Optional[float] = None   # None -> hidden size (rbf / normprod)
     n_clusters: Optional[int] = None         # fixed children per parent instead of the eigenvalue threshold
+    discretise: Literal["kmeans", "axis_align"] = "kmeans"   # axis_align = kway_ncut (modeling_spectral.py:136-138)
     kmeans_iters: int = 100
     eig_iters: int = 60
     eig_tol: float = 2e-5
@@ -58,7 +59,7 @@ class SpectralClustering(ClusteringModule):
         return F.cluster_tokens(
             x, parent_indices, ncut_dim=c.ncut_dim, n_clusters=c.n_clusters, eigenvalue_threshold=thr,
             mode=c.ncut_dist or "rbf", gamma=c.affinity_focal_gamma, scale=c.distance_scale,
-            kmeans_iters=c.kmeans_iters, eig_iters=c.eig_iters, eig_tol=c.eig_tol,
+            kmeans_iters=c.kmeans_iters, eig_iters=c.eig_iters, eig_tol=c.eig_tol, discretise=c.discretise,
             n_parents=kwargs.get("n_parents"), want_pool=kwargs.get("want_pool", False),
             pool_k=kwargs.get("pool_k"))
 

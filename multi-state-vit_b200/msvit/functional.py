@@ -66,11 +66,14 @@ class ClusterPlan:
                  n_clusters: Optional[int] = None, eigenvalue_threshold: Optional[float] = None, mode: str = "rbf",
                  gamma: float = 3.0, scale: Optional[float] = None, n_parents: int = 1, kmeans_iters: int = 100,
                  eig_iters: int = 60, eig_tol: float = 2e-5, oversample: int = 8, pool_k: Optional[int] = None,
-                 want_pool: bool = True, fused: Optional[bool] = None):
+                 want_pool: bool = True, fused: Optional[bool] = None, discretise: str = "kmeans"):
         if mode not in _lib.DIST:
             raise ValueError(f"unknown distance {mode!r}")
         if n_clusters is None and eigenvalue_threshold is None:
             raise ValueError("give n_clusters or eigenvalue_threshold")
+        if discretise not in _lib.DISC:
+            raise ValueError(f"unknown discretisation {discretise!r} (kmeans | axis_align)")
+        self.disc = _lib.DISC[discretise]
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("msvit.cluster_tokens runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -177,7 +180,7 @@ class ClusterPlan:
                 mark(3)
                 check(lib.msvit_ritz_kmeans(p(self.U), p(self.H), p(self.info), p(self.deg), p(self.V), p(self.lam), None,
                                             p(self.child), p(self.n_child), rows, S, N, k, self.block, self.n_converge,
-                                            self.nk, self.thr, self.kmeans_iters, st), "msvit_ritz_kmeans")
+                                            self.nk, self.thr, self.kmeans_iters, self.disc, st), "msvit_ritz_kmeans")
                 mark(4)
             else:
                 check(lib.msvit_affinity_degree(p(xs), self.dtype_code, p(self.A), p(self.deg), rows, S, N, D, self.mode,
@@ -188,9 +191,9 @@ class ClusterPlan:
                                          self.block, self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge,
                                          p(self.seg_off), p(self.a_off), st), "msvit_ncut_eig")
                 mark(3)
-                check(lib.msvit_kmeans(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted), p(self.n_child),
-                                       None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters, p(self.seg_off), st),
-                      "msvit_kmeans")
+                check(lib.msvit_discretise(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted),
+                                           p(self.n_child), None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters,
+                                           self.disc, p(self.seg_off), st), "msvit_discretise")
                 mark(4)
                 check(lib.msvit_compose_labels(p(self.labels_sorted), p(self.n_child), p(self.perm), p(self.seg_off),
                                                p(self.child), B, N, P, st), "msvit_compose_labels")
@@ -222,7 +225,8 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
                    mode: str = "rbf", gamma: float = 3.0, scale: Optional[float] = None,
                    n_parents: Optional[int] = None, kmeans_iters: int = 100, eig_iters: int = 60,
                    eig_tol: float = 2e-5, oversample: int = 8, pool_k: Optional[int] = None,
-                   want_pool: bool = True, keep_affinity: bool = False, fused: Optional[bool] = None) -> ClusterOutput:
+                   want_pool: bool = True, keep_affinity: bool = False, fused: Optional[bool] = None,
+                   discretise: str = "kmeans") -> ClusterOutput:
     """One-shot form: builds a ClusterPlan for x's shape and runs it (buffers are owned by the result)."""
     if x.dim() != 3:
         raise ValueError("x must be [batch, tokens, hidden]")
@@ -245,7 +249,8 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
     plan = ClusterPlan(B, N, D, x.dtype, x.device, ncut_dim=ncut_dim, n_clusters=n_clusters,
                        eigenvalue_threshold=eigenvalue_threshold, mode=mode, gamma=gamma, scale=scale, n_parents=P,
                        kmeans_iters=kmeans_iters, eig_iters=eig_iters, eig_tol=eig_tol, oversample=oversample,
-                       pool_k=pool_k, want_pool=want_pool, fused=False if keep_affinity else fused)
+                       pool_k=pool_k, want_pool=want_pool, fused=False if keep_affinity else fused,
+                       discretise=discretise)
     out = plan.run(x, parent_indices)
     if not keep_affinity:
         out.affinity = None

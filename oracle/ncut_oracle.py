@@ -18,6 +18,8 @@ What each function follows (paths relative to /root/reference):
                                 model/clustering/modeling_spectral.py:54-61 (gamma = 3.0, rbf|cosine)
   ncut_eig                      sandbox/test.py:114-118 (deg, I - D^-1/2 A D^-1/2, eigh, leading k)
   select_n_children             model/clustering/modeling_spectral.py:87,92-93
+  kway_ncut                     model/clustering/modeling_spectral.py:136-138, modeling_axisalign.py:35-36 (third-party
+                                algorithm, restated from Yu & Shi 2003; unpinned)
   kmeans                        model/clustering/modeling_spectral.py:90 (Lloyd on V[:, :K]),
                                 :129 (assignment = argmin cdist), :125-133,271-278 (centre = label mean,
                                 centroid-seeded k-means)
@@ -172,6 +174,43 @@ def kmeans(P: torch.Tensor, K: int, init: Optional[torch.Tensor] = None, weight:
     return labels, C[order], int(order.numel())
 
 
+# --------------------------------------------------------------------------- axis-aligned discretisation
+def kway_ncut(V: torch.Tensor, K: int, weight: Optional[torch.Tensor] = None, iters: int = 100):
+    """Axis-aligned discretisation of a spectral embedding: rows of V[:, :K] -> (labels [n] canonical, C, R [K, K]).
+
+    UNPINNED (third-party algorithm): the reference calls ncut_pytorch.kway_ncut
+    (model/clustering/modeling_spectral.py:136-138, model/clustering/modeling_axisalign.py:35-36), which is absent from
+    the checkout; this restates the published algorithm it implements, Yu & Shi, "Multiclass spectral clustering"
+    (ICCV 2003): scale the rows to unit length, pick K rows greedily as orthogonal as possible for the initial
+    rotation, then alternate  labels = argmax(Xn R)  and  R = V U^T  with  onehot(labels)^T Xn = U S V^T.
+    Deterministic choices of this repository: first row = argmax weight (row 0 without weights), ties -> lowest index,
+    stop when the labels stop changing, first-occurrence relabelling.
+    """
+    n = V.shape[0]
+    K = max(1, min(int(K), n, V.shape[1]))
+    X = V[:, :K]
+    nrm = X.norm(dim=1, keepdim=True)
+    Xn = torch.where(nrm > 0, X / nrm.clamp_min(1e-300), torch.zeros_like(X))
+    first = int(torch.argmax(weight).item()) if weight is not None else 0
+    R = torch.zeros(K, K, dtype=X.dtype)
+    R[:, 0] = Xn[first]
+    c = torch.zeros(n, dtype=X.dtype)
+    for j in range(1, K):
+        c = c + (Xn @ R[:, j - 1]).abs()
+        R[:, j] = Xn[int(torch.argmin(c).item())]
+    labels = torch.full((n,), -1, dtype=torch.long)
+    for _ in range(max(1, iters)):
+        new = torch.argmax(Xn @ R, dim=1)
+        if torch.equal(new, labels):
+            break
+        labels = new
+        M = torch.zeros(K, K, dtype=X.dtype).index_add_(0, labels, Xn)      # onehot(labels)^T Xn
+        U, S, Vh = torch.linalg.svd(M)
+        R = Vh.T @ U.T
+    labels, order = canonical_relabel(labels)
+    return labels, int(order.numel()), R
+
+
 # --------------------------------------------------------------------------- pooling
 def pool(x: torch.Tensor, labels: torch.Tensor, K: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """x [B, N, D], labels [B, N] -> pooled [B, K, D] (cluster means, empty -> 0), counts [B, K] int32.
@@ -191,7 +230,7 @@ def pool(x: torch.Tensor, labels: torch.Tensor, K: int) -> Tuple[torch.Tensor, t
 
 # --------------------------------------------------------------------------- whole path
 def cluster_segment(xs: torch.Tensor, k: int, n_clusters: Optional[int], threshold: Optional[float],
-                    mode: str, gamma: float, scale: Optional[float], kmeans_iters: int):
+                    mode: str, gamma: float, scale: Optional[float], kmeans_iters: int, discretise: str = "kmeans"):
     """One (image, parent) segment xs [n, D] -> (labels_local [n], C, V [n,k], lam [k])."""
     n = xs.shape[0]
     A = affinity(xs, mode, gamma, scale)
@@ -201,14 +240,17 @@ def cluster_segment(xs: torch.Tensor, k: int, n_clusters: Optional[int], thresho
     else:
         K = select_n_children(lam, float(threshold))
     K = max(1, min(K, n, k))
-    labels, _, C = kmeans(V[:, :K], K, weight=deg, iters=kmeans_iters)
+    if discretise == "axis_align":
+        labels, C, _ = kway_ncut(V, K, weight=deg, iters=kmeans_iters)
+    else:
+        labels, _, C = kmeans(V[:, :K], K, weight=deg, iters=kmeans_iters)
     return labels, C, V, lam
 
 
 def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, *, ncut_dim: int,
                    n_clusters: Optional[int] = None, eigenvalue_threshold: Optional[float] = None,
                    mode: str = "rbf", gamma: float = 3.0, scale: Optional[float] = None,
-                   kmeans_iters: int = 100):
+                   kmeans_iters: int = 100, discretise: str = "kmeans"):
     """Per-(image, parent) NCut clustering.
 
     x [B, N, D]; parent_indices [B, N] int64 (None = all zeros).
@@ -232,7 +274,7 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
             if idx.numel() == 0:
                 continue
             labels, C, V, lam = cluster_segment(x[b, idx], ncut_dim, n_clusters, eigenvalue_threshold,
-                                                mode, gamma, scale, kmeans_iters)
+                                                mode, gamma, scale, kmeans_iters, discretise)
             child[b, idx] = offset + labels
             eigvecs[b, idx] = V
             eigvals[b, p] = lam

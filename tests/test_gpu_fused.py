@@ -168,3 +168,33 @@ def test_plan_replays_in_a_cuda_graph_and_c1_latency():
     replay = timed(graph.replay)
     print(f"C1 (B=8) latency: eager launches {eager * 1e3:.1f} us, CUDA-graph replay {replay * 1e3:.1f} us")
     assert replay <= eager * 1.5
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_axis_aligned_discretisation_matches_oracle(fused):
+    """kway_ncut (modeling_spectral.py:136-138) as the alternative to k-means, on both paths."""
+    B, N, D, K = 6, 196, 768, 8
+    x, planted = planted_tokens(B, N, D, K)
+    out = msvit.cluster_tokens(x.to(DEV), ncut_dim=K, n_clusters=K, scale=default_scale(D), fused=fused,
+                               discretise="axis_align")
+    child, _, _, nc = O.cluster_tokens(O.round_to_tf32(x).double(), None, ncut_dim=K, n_clusters=K,
+                                       scale=default_scale(D), discretise="axis_align")
+    assert out.n_child.cpu().tolist() == nc.tolist()
+    assert torch.equal(out.labels.cpu(), child)
+    for b in range(B):
+        assert torch.equal(O.canonical_relabel(planted[b])[0], out.labels[b].cpu())
+    # odd number of clusters, ragged hierarchy (two-kernel path), eigenvalue-threshold selection
+    x2, _ = planted_tokens(3, 150, 96, 5)
+    o2 = msvit.cluster_tokens(x2.to(DEV), ncut_dim=6, eigenvalue_threshold=0.05, scale=default_scale(96), fused=fused,
+                              discretise="axis_align")
+    c2, _, _, n2 = O.cluster_tokens(O.round_to_tf32(x2).double(), None, ncut_dim=6, eigenvalue_threshold=0.05,
+                                    scale=default_scale(96), discretise="axis_align")
+    assert o2.n_child.cpu().tolist() == n2.tolist() and torch.equal(o2.labels.cpu(), c2)
+    if not fused:
+        parent = torch.zeros(3, 150, dtype=torch.long)
+        parent[:, 75:] = 1
+        o3 = msvit.cluster_tokens(x2.to(DEV), parent.to(DEV), ncut_dim=4, n_clusters=3, scale=default_scale(96),
+                                  discretise="axis_align")
+        c3, _, _, n3 = O.cluster_tokens(O.round_to_tf32(x2).double(), parent, ncut_dim=4, n_clusters=3,
+                                        scale=default_scale(96), discretise="axis_align")
+        assert o3.n_child.cpu().tolist() == n3.tolist() and torch.equal(o3.labels.cpu(), c3)

@@ -166,3 +166,21 @@ def test_attention_mask_structure():
     one = m[1]
     assert one[R0, T0] and not one[R1, T0] and not one[R0, T1]   # image 1 has a single live cluster
     assert not one[T1].any() and one[T0, a] and one[a, R0]
+
+
+def test_kway_ncut_recovers_a_planted_partition_and_is_rotation_invariant():
+    # axis-aligned discretisation (Yu & Shi 2003; ncut_pytorch.kway_ncut at modeling_spectral.py:136-138): on a clean
+    # planted mixture it recovers the partition, and rotating the embedding columns does not change the labels
+    from msvit.synthetic import default_scale, planted_image
+    x, lab = planted_image(3, 120, 64, 5)
+    A = O.affinity(x.double(), "rbf", 3.0, default_scale(64))
+    V, lam, deg = O.ncut_eig(A, 5)
+    labels, C, R = O.kway_ncut(V, 5, weight=deg)
+    assert C == 5 and torch.equal(labels, O.canonical_relabel(lab)[0])
+    assert torch.allclose(R.T @ R, torch.eye(5, dtype=R.dtype), atol=1e-9)          # a rotation
+    Q, _ = torch.linalg.qr(torch.randn(5, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(0)))
+    labels_rot, C_rot, _ = O.kway_ncut(V @ Q, 5, weight=deg)
+    assert C_rot == 5 and torch.equal(labels_rot, labels)
+    # same partition as k-means on this embedding
+    km, _, _ = O.kmeans(V[:, :5], 5, weight=deg)
+    assert torch.equal(km, labels)
