@@ -297,6 +297,24 @@ def run_ours(args):
     if not torch.equal(res.labels, out.labels.cpu()):
         raise RuntimeError("end-to-end labels differ from the device-resident run")
 
+    # ---- the other BASELINE.json configs as sub-records (C3, C4 with its three levels, C5 with its NCCL all-reduce)
+    extras = {}
+    h2d_bytes, d2h_bytes = hc.h2d_bytes, hc.d2h_bytes
+    if args.extras and args.config == "C2":
+        del hc
+        torch.cuda.empty_cache()
+        for nm in ("C3", "C4"):
+            try:
+                extras[nm] = extra_per_image(nm, dev, world, rank, max(3, args.steps // 4), 3, barrier, reduce_max)
+            except Exception as exc:  # a sub-record must not take the headline down
+                extras[nm] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            c5 = c5_measure(args, dev, world, rank, local, max(5, args.steps // 2), 3, with_e2e=False)
+            if c5 is not None:
+                extras["C5"] = {k_: c5[k_] for k_ in ("metric", "value", "unit", "ms_per_step", "scaling", "roofline", "stages")}
+                extras["C5"]["workload"] = c5["config"]["workload"]
+        except Exception as exc:
+            extras["C5"] = {"error": f"{type(exc).__name__}: {exc}"}
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -369,14 +387,78 @@ def run_ours(args):
                          "sample": f"{cpu_n} images of {args.config} in batches of 8 ({cpu_s:.1f} s), "
                                    f"torch CPU oracle, {cores} threads"},
         "e2e": {"value": round(world * B * e2e_steps / e2e_ms * 1e3, 1), "unit": UNIT,
-                "h2d_bytes_per_step": hc.h2d_bytes, "d2h_bytes_per_step": hc.d2h_bytes, "steps": e2e_steps,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                 "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "msvit.HostClusterer.run (pinned host buffers)"},
         "gpu_launches": n_launch_step * args.steps,
         "clocks": clocks,
     }
+    if extras:
+        line["extra_configs"] = extras
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ the other configs
+def extra_per_image(name, dev, world, rank, steps, warmup, barrier, reduce_max):
+    """C3 (ViT-L/14, 576 tokens, k=16) and C4 (1024 tokens, THREE hierarchical levels: 1 -> 4 -> 16 parents per image,
+    every parent segment re-clustered into 4 children from that level's hidden states) as sub-records of the main
+    line: device-resident images/s per GPU batch, weak scaling, per-stage ms."""
+    from msvit.functional import ClusterPlan
+    from msvit.synthetic import default_scale, planted_tokens
+    B, N, D, K, k = workload(name)
+    pool_n = min(B, 32)
+    xs, _ = planted_tokens(pool_n, N, D, K, first=rank * pool_n)
+    x = xs.repeat((B + pool_n - 1) // pool_n, 1, 1)[:B].contiguous().to(dev)
+    scale = default_scale(D)
+    if name != "C4":
+        plans = [ClusterPlan(B, N, D, torch.float32, dev, ncut_dim=k, n_clusters=K, scale=scale)]
+        levels = [x]
+    else:
+        # level l clusters every parent of level l-1 into K children: P = 1, K, K^2 parents
+        plans = [ClusterPlan(B, N, D, torch.float32, dev, ncut_dim=k, n_clusters=K, scale=scale, n_parents=K ** l,
+                             want_pool=(l == 2), pool_k=K ** 3) for l in range(3)]
+        g = torch.Generator(device=dev).manual_seed(77 + rank)
+        levels = [x] + [x + 0.1 * torch.randn(x.shape, generator=g, device=dev) for _ in range(2)]
+
+    def step(ev=None):
+        parent = None
+        outs = []
+        for l, plan in enumerate(plans):
+            out = plan.run(levels[l], parent, events=None if ev is None else ev[l])
+            parent = out.labels
+            outs.append(out)
+        return outs
+
+    for _ in range(warmup):
+        outs = step()
+    barrier()
+    n_st = len(ClusterPlan.STAGES)
+    events = [[[torch.cuda.Event(enable_timing=True) for _ in range(n_st + 1)] for _ in plans] for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for s_ in range(steps):
+        outs = step(events[s_])
+    t1.record()
+    barrier()
+    ms = reduce_max(t0.elapsed_time(t1)) / steps
+    stage_ms = {}
+    for l in range(len(plans)):
+        for i, nm in enumerate(ClusterPlan.STAGES):
+            v = sum(ev[l][i].elapsed_time(ev[l][i + 1]) for ev in events) / steps
+            if v > 0:
+                stage_ms[nm if len(plans) == 1 else f"L{l}.{nm}"] = round(v, 4)
+    rec = {"value": round(world * B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "scaling": "weak",
+           "workload": workload_string(name, B, N, D, K, k, "float32") +
+                       (" -- 3 hierarchical levels (1, 4, 16 parents per image)" if name == "C4" else ""),
+           "stages_ms": stage_ms, "eig_iters_mean": [round(float(o.iters.float().mean()), 2) for o in outs],
+           "converged": [bool(o.converged.all()) for o in outs]}
+    if name == "C4":
+        rec["children_per_image"] = [round(float((o.labels.max(dim=1).values + 1).float().mean()), 2) for o in outs]
+    del plans, levels, x
+    torch.cuda.empty_cache()
+    return rec
 
 
 # ------------------------------------------------------------------------------------------ C5: dataset-level k-means
@@ -389,8 +471,6 @@ def run_c5(args):
     all-reduce of the packed [k, D+1] sums|counts buffer (3.08 MB) over NCCL."""
     import torch.distributed as dist
     import msvit
-    from msvit.global_kmeans import GlobalKMeansPlan, broadcast_init, global_kmeans
-    from msvit.sharding import max_over_ranks, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -402,6 +482,18 @@ def run_c5(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     msvit._lib.load()
+    line = c5_measure(args, dev, world, rank, local, args.steps, args.warmup, with_e2e=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def c5_measure(args, dev, world, rank, local, steps, warmup, with_e2e):
+    """The C5 measurement proper (all ranks call it; rank 0 gets the record, the others None)."""
+    import torch.distributed as dist
+    from msvit.global_kmeans import GlobalKMeansPlan, broadcast_init, global_kmeans
+    from msvit.sharding import max_over_ranks, shard_bounds
     n_total, D, k = args.c5_rows, 768, 1000
     first, n = shard_bounds(n_total, rank, world)
     dtype = torch.bfloat16   # the dataset-level path takes bf16 features
@@ -436,43 +528,48 @@ def run_c5(args):
         if ev is not None:
             ev[5].record()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
-    for s in range(args.steps):
+    for s in range(steps):
         step(events[s])
     t1.record()
     barrier()
     ms_total = max_over_ranks(t0.elapsed_time(t1), dev)
     clocks = sampler.stop() if rank == 0 else None
-    stage_ms = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in events) / args.steps for i, nm in enumerate(names)}
+    stage_ms = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in events) / steps for i, nm in enumerate(names)}
 
     # end to end: the public call on HOST features (H2D of the shard, `steps` iterations, D2H of centroids and labels)
-    host = x.cpu().pin_memory()
-    barrier()
-    w0 = time.perf_counter()
-    res = global_kmeans(host.to(dev, non_blocking=True), k, args.steps, init=plan.centroids.clone())
-    cent_h, lab_h = res.centroids.cpu(), res.labels.cpu()
-    barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - w0), dev)
+    e2e = None
+    if with_e2e:
+        host = x.cpu().pin_memory()
+        barrier()
+        w0 = time.perf_counter()
+        res = global_kmeans(host.to(dev, non_blocking=True), k, steps, init=plan.centroids.clone())
+        cent_h, lab_h = res.centroids.cpu(), res.labels.cpu()
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - w0), dev)
+        e2e = {"value": round(n_total * steps / e2e_ms * 1e3, 1), "unit": "rows/s",
+               "h2d_bytes_per_step": host.numel() * 2 // steps,
+               "d2h_bytes_per_step": (cent_h.numel() * 4 + lab_h.numel() * 8) // steps,
+               "api": "msvit.global_kmeans on host features (one H2D, steps iterations, D2H of centroids + labels)"}
+    del x
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peaks = load_peaks()
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     flops = 2.0 * n * k * D
     ach = flops / stage_ms["assign"] / 1e9
     line = {
         "metric": C5_METRIC, "value": round(n_total / ms_step * 1e3, 1), "unit": "rows/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"C5: {n_total} x {D} bf16 features, k={k}, rows sharded x{world} ({n} on rank 0), "
                                f"one all-reduce of {plan.allreduce_bytes} B per iteration",
@@ -483,16 +580,10 @@ def run_c5(args):
                      "peak_source": peaks["_source"] + ", sustained bf16",
                      "share_of_step": round(stage_ms["assign"] / sum(stage_ms.values()), 3)},
         "stages": {nm: {"ms": round(v, 4)} for nm, v in stage_ms.items()},
-        "e2e": {"value": round(n_total * args.steps / e2e_ms * 1e3, 1), "unit": "rows/s",
-                "h2d_bytes_per_step": host.numel() * 2 // args.steps,
-                "d2h_bytes_per_step": (cent_h.numel() * 4 + lab_h.numel() * 8) // args.steps,
-                "api": "msvit.global_kmeans on host features (one H2D, steps iterations, D2H of centroids + labels)"},
-        "gpu_launches": 6 * args.steps, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": 6 * steps, "clocks": clocks,
     }
     line["stages"]["accumulate"]["GB/s"] = round((n * D * 2 + n * 4 + k * (D + 1) * 4) / stage_ms["accumulate"] / 1e6, 1)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -509,6 +600,8 @@ def main():
     ap.add_argument("--ref-images-per-step", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
     ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the C3 / C4 / C5 sub-records of the default (C2) run")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -49,7 +49,7 @@ for what in "$@"; do
       echo "c5 x$NG rc=$?"; grep '^{' gpurun_out/bench_c5x$NG.json | cut -c1-1300; tail -2 gpurun_out/bench_c5x$NG.err
       ;;
     launches)
-      CMD="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --cpu-images 8"
+      CMD="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --cpu-images 8 --no-extras"
       timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
       timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
           --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
@@ -57,7 +57,7 @@ for what in "$@"; do
       ;;
     full:*)
       KREGEX="${what#full:}"
-      CMD="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --cpu-images 8"
+      CMD="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --cpu-images 8 --no-extras"
       timeout 600 $CMD > gpurun_out/plain_full.log 2>&1 &&
       timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 3 -c 1 \
           -f -o "gpurun_out/prof_${KREGEX}" $CMD > gpurun_out/ncu_full_${KREGEX}.log 2>&1
