@@ -230,6 +230,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     msvit._lib.load()  # fail loudly if libmsvit.so is missing
+    # host threads and the pinned buffers they allocate stay on the NUMA node of this rank's GPU
+    from msvit.sharding import bind_host_thread_to_gpu
+    numa_cores = bind_host_thread_to_gpu(local)
 
     B, N, D, K, k = workload(args.config)
     dtype = torch.float32 if args.dtype == "float32" else torch.bfloat16
@@ -296,6 +299,28 @@ def run_ours(args):
     # the end-to-end results agree with the device-resident ones
     if not torch.equal(res.labels, out.labels.cpu()):
         raise RuntimeError("end-to-end labels differ from the device-resident run")
+    # same call with the host tokens held in bf16 (the caller's choice of a narrower host dtype): half the H2D bytes,
+    # kind::f16 tensor-core path on the device
+    e2e_bf16 = None
+    if dtype == torch.float32 and args.extras:
+        del hc
+        host16 = host.to(torch.bfloat16).pin_memory()
+        hc = HostClusterer(B, N, D, torch.bfloat16, dev, ncut_dim=k, n_clusters=K, scale=scale, chunk=args.e2e_chunk)
+        for _ in range(2):
+            res16 = hc.run(host16)
+        barrier()
+        b0_, b1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        b0_.record()
+        for s in range(e2e_steps):
+            res16 = hc.run(host16)
+        b1_.record()
+        barrier()
+        ms16 = reduce_max(max(b0_.elapsed_time(b1_), 1e3 * (time.perf_counter() - w0)))
+        e2e_bf16 = {"value": round(world * B * e2e_steps / ms16 * 1e3, 1), "unit": UNIT, "h2d_bytes_per_step": hc.h2d_bytes,
+                    "d2h_bytes_per_step": hc.d2h_bytes, "ms_per_step": round(ms16 / e2e_steps, 3),
+                    "labels_equal_fp32_run": bool(torch.equal(res16.labels, res.labels))}
+        del host16
 
     # ---- the other BASELINE.json configs as sub-records (C3, C4 with its three levels, C5 with its NCCL all-reduce)
     extras = {}
@@ -388,7 +413,12 @@ def run_ours(args):
                                    f"torch CPU oracle, {cores} threads"},
         "e2e": {"value": round(world * B * e2e_steps / e2e_ms * 1e3, 1), "unit": UNIT,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "msvit.HostClusterer.run (pinned host buffers)"},
+                "ms_per_step": round(e2e_ms / e2e_steps, 3), "api": "msvit.HostClusterer.run (pinned host buffers)",
+                "h2d_GB/s_per_gpu": round(h2d_bytes * e2e_steps / e2e_ms / 1e6, 1),
+                "host_cores_bound": None if numa_cores is None else len(numa_cores),
+                "note": "fp32 host tokens (the reference hands fp32 hidden states): 617 MB per GPU and step cross PCIe, "
+                        "which is the ceiling of this number (profiles/r2_h2d_probe.md); e2e_bf16_host halves the bytes"},
+        "e2e_bf16_host": e2e_bf16,
         "gpu_launches": n_launch_step * args.steps,
         "clocks": clocks,
     }
@@ -599,7 +629,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=2048, help="images in the cpu_baseline sample")
     ap.add_argument("--ref-images-per-step", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
-    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--e2e-chunk", type=int, default=148, help="images per H2D chunk (one CTA per SM per chunk)")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the C3 / C4 / C5 sub-records of the default (C2) run")
     args = ap.parse_args()

@@ -41,3 +41,43 @@ def max_over_ranks(value: float, device: torch.device, group: Optional[dist.Proc
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def bind_host_thread_to_gpu(device_index: int) -> Optional[List[int]]:
+    """Pin the calling host thread to the CPU cores next to GPU `device_index` (the "CPU Affinity" column of
+    `nvidia-smi topo -m`), so that pinned buffers allocated afterwards are first-touched on that GPU's NUMA node and
+    the H2D / D2H copies do not cross the socket interconnect.  Best effort: returns the core list, or None when the
+    topology cannot be read (the caller just keeps its affinity)."""
+    import os
+    import subprocess
+    try:
+        txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    cores: List[int] = []
+    for line in txt.splitlines():
+        f = line.split()
+        if not f or f[0] != f"GPU{device_index}":
+            continue
+        # the affinity field looks like "0-31,64-95"
+        for tok in f[1:]:
+            if tok and tok[0].isdigit() and all(ch.isdigit() or ch in "-," for ch in tok) and ("-" in tok or "," in tok):
+                try:
+                    for part in tok.split(","):
+                        a, _, b = part.partition("-")
+                        cores.extend(range(int(a), int(b or a) + 1))
+                    break
+                except ValueError:
+                    cores = []
+        break
+    if not cores:
+        return None
+    try:
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cores) & allowed)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return use
+    except (AttributeError, OSError):
+        return None
