@@ -610,7 +610,7 @@ def c5_measure(args, dev, world, rank, local, steps, warmup, with_e2e):
                      "peak_source": peaks["_source"] + ", sustained bf16",
                      "share_of_step": round(stage_ms["assign"] / sum(stage_ms.values()), 3)},
         "stages": {nm: {"ms": round(v, 4)} for nm, v in stage_ms.items()},
-        "e2e": e2e, "gpu_launches": 6 * steps, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": 7 * steps, "clocks": clocks,
     }
     line["stages"]["accumulate"]["GB/s"] = round((n * D * 2 + n * 4 + k * (D + 1) * 4) / stage_ms["accumulate"] / 1e6, 1)
     return line

@@ -160,7 +160,8 @@ int msvit_compose_labels(const int32_t* labels_sorted, const int32_t* n_child, c
  * msvit_gkm_sort: stable counting sort of row ids by label: perm [n] (rows grouped by label, ascending row id
  *   inside a label), seg_off [k+1].  workspace: msvit_gkm_workspace_bytes(n, k) bytes.  k <= 12000.
  * msvit_gkm_accumulate: packed [k, D+1] fp32: columns [0, D) = sum of the member rows (fixed order, no atomics),
- *   column D = member count.
+ *   column D = member count.  workspace (msvit_gkm_accumulate_workspace_bytes(k, D) bytes, may be NULL): partial sums
+ *   of the runs every centroid's rows are cut into, so that very unequal clusters do not serialise on one CTA.
  * msvit_gkm_finalize: centroids [k, D] fp32 (in/out) = sum / count where count > 0 (an empty cluster keeps its
  *   centre); centroids_op [k, D] in op_dtype (may be NULL) = the tensor-core operand copy. */
 int msvit_gkm_assign(const void* x, int x_dtype, const void* centroids_op, int32_t* labels, float* best, int64_t n,
@@ -168,8 +169,9 @@ int msvit_gkm_assign(const void* x, int x_dtype, const void* centroids_op, int32
 size_t msvit_gkm_workspace_bytes(int64_t n, int k);
 int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* perm, int32_t* seg_off, void* workspace,
                    size_t workspace_bytes, msvit_stream_t stream);
+size_t msvit_gkm_accumulate_workspace_bytes(int k, int D);
 int msvit_gkm_accumulate(const void* x, int x_dtype, const int32_t* perm, const int32_t* seg_off, float* packed,
-                         int64_t n, int k, int D, msvit_stream_t stream);
+                         int64_t n, int k, int D, void* workspace, size_t workspace_bytes, msvit_stream_t stream);
 int msvit_gkm_finalize(const float* packed, float* centroids, void* centroids_op, int op_dtype, int k, int D,
                        msvit_stream_t stream);
 

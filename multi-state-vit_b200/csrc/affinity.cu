@@ -90,7 +90,8 @@ affinity_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_consta
                 const Params P) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array itself keeps the shared state space: LDS / STS instead of generic accesses)
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Shared& sh = *reinterpret_cast<Shared*>(tiles + static_cast<size_t>(P.stages) * P.stage_bytes);
 
   const int warp = threadIdx.x >> 5;

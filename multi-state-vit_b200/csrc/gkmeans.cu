@@ -57,7 +57,8 @@ template <bool TF32>
 __global__ void __launch_bounds__(kThreads, 1)
 assign_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c, const Params P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array itself keeps the shared state space: LDS / STS instead of generic accesses)
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Shared& sh = *reinterpret_cast<Shared*>(tiles + static_cast<size_t>(kStages) * kStageBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -228,6 +229,7 @@ assign_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 
 // ----------------------------------------------------------------------------- stable counting sort by label
 constexpr int kSortRows = 2048;     // rows per sort block (one warp each)
+constexpr int kAccParts = 8;        // runs the member rows of a centroid are cut into (accumulate_bulk_kernel)
 
 // hist[b][c] = number of rows of block b with label c (labels outside [0, k) are dropped)
 __global__ void __launch_bounds__(128) hist_kernel(const int32_t* __restrict__ labels, int n, int k,
@@ -245,36 +247,70 @@ __global__ void __launch_bounds__(128) hist_kernel(const int32_t* __restrict__ l
   for (int c = threadIdx.x; c < k; c += blockDim.x) hist[static_cast<size_t>(b) * k + c] = cnt[c];
 }
 
-// one thread per label: running offsets over the blocks; seg_off = exclusive scan of the label totals
-__global__ void __launch_bounds__(256) scan_kernel(int32_t* __restrict__ hist, int nb, int k,
-                                                   int32_t* __restrict__ seg_off) {
-  __shared__ int32_t tot[1024];
+// Offsets of the blocks inside each label, many CTAs: one thread per label walks the blocks (eight independent loads
+// at a time), hist[b][c] <- number of rows of label c in the blocks before b, tot[c] = the label's row count.
+// The workspace holds the label totals behind the histograms.
+__global__ void __launch_bounds__(64) block_offsets_kernel(int32_t* __restrict__ hist, int nb, int k,
+                                                          int32_t* __restrict__ tot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  int run = 0;
+  int b = 0;
+  for (; b + 8 <= nb; b += 8) {
+    int v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = hist[static_cast<size_t>(b + i) * k + c];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hist[static_cast<size_t>(b + i) * k + c] = run;
+      run += v[i];
+    }
+  }
+  for (; b < nb; ++b) {
+    const int v = hist[static_cast<size_t>(b) * k + c];
+    hist[static_cast<size_t>(b) * k + c] = run;
+    run += v;
+  }
+  tot[c] = run;
+}
+
+// seg_off = exclusive scan of the label totals (one CTA, 1024 labels per pass)
+__global__ void __launch_bounds__(1024) label_scan_kernel(const int32_t* __restrict__ tot, int k,
+                                                          int32_t* __restrict__ seg_off) {
+  __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int c0 = 0; c0 < k; c0 += 1024) {
-    // totals of 1024 labels at a time
-    for (int c = c0 + threadIdx.x; c < min(k, c0 + 1024); c += blockDim.x) {
-      int s = 0;
-      for (int b = 0; b < nb; ++b) {
-        const int v = hist[static_cast<size_t>(b) * k + c];
-        hist[static_cast<size_t>(b) * k + c] = s;  // offset of block b inside label c
-        s += v;
+    const int c = c0 + threadIdx.x;
+    const int v = c < k ? tot[c] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_tot[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
       }
-      tot[c - c0] = s;
+      warp_tot[lane] = wi - w;   // exclusive prefix of the warp totals
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int run = carry;
-      for (int c = c0; c < min(k, c0 + 1024); ++c) {
-        seg_off[c] = run;
-        run += tot[c - c0];
-      }
-      carry = run;
-      if (c0 + 1024 >= k) seg_off[k] = run;
-    }
+    const int base = carry + warp_tot[warp];
+    if (c < k) seg_off[c] = base + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = base + incl;
     __syncthreads();
   }
+  if (threadIdx.x == 0) seg_off[k] = carry;
 }
 
 // perm[seg_off[c] + hist[b][c] + rank of the row among the block's rows with label c] = row   (one warp per block)
@@ -332,14 +368,21 @@ __global__ void __launch_bounds__(512) accumulate_kernel(const T* __restrict__ x
   float acc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  // four member rows in flight per thread; the row ids of a batch are loaded first (they are the addresses of the
+  // feature loads), so that one round trip to memory covers four rows instead of one
   int r = s0 + j;
-  for (; r + RL < s1; r += 2 * RL) {
-    const uint4 a = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(perm[r]) * D + ct * V);
-    const uint4 b = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(perm[r + RL]) * D + ct * V);
+  for (; r + 3 * RL < s1; r += 4 * RL) {
+    const int i0 = perm[r], i1 = perm[r + RL], i2 = perm[r + 2 * RL], i3 = perm[r + 3 * RL];
+    const uint4 a = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(i0) * D + ct * V);
+    const uint4 b = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(i1) * D + ct * V);
+    const uint4 c4 = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(i2) * D + ct * V);
+    const uint4 d4 = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(i3) * D + ct * V);
     add_row<T>(acc, a);
     add_row<T>(acc, b);
+    add_row<T>(acc, c4);
+    add_row<T>(acc, d4);
   }
-  if (r < s1) add_row<T>(acc, *reinterpret_cast<const uint4*>(x + static_cast<size_t>(perm[r]) * D + ct * V));
+  for (; r < s1; r += RL) add_row<T>(acc, *reinterpret_cast<const uint4*>(x + static_cast<size_t>(perm[r]) * D + ct * V));
 #pragma unroll
   for (int i = 0; i < V; ++i) part[j * D + ct * V + i] = acc[i];
   __syncthreads();
@@ -350,6 +393,90 @@ __global__ void __launch_bounds__(512) accumulate_kernel(const T* __restrict__ x
     out[d] = s;
   }
   if (threadIdx.x == 0) out[D] = static_cast<float>(s1 - s0);
+}
+
+// Same sums with the member rows fetched by asynchronous bulk copies (cp.async.bulk global -> shared, mbarrier
+// completion): the row gather is pure memory latency (ncu: long-scoreboard stalls 41 per issue, 1.5 TB/s with
+// register loads), so every CTA keeps two batches of R whole rows in flight without holding a register for them.
+// One CTA per centroid, one thread per 16-byte column chunk; a thread adds its chunk of the rows in sorted order
+// (one accumulator per column: fixed order, no atomics, no cross-thread reduction).
+template <typename T>
+__global__ void __launch_bounds__(256) accumulate_bulk_kernel(const T* __restrict__ x, const int32_t* __restrict__ perm,
+                                                              const int32_t* __restrict__ seg_off, int D, int R,
+                                                              int parts, float* __restrict__ packed,
+                                                              float* __restrict__ partial) {
+  constexpr int V = 16 / sizeof(T);
+  extern __shared__ __align__(128) uint8_t rows_sm[];   // [2][R][row bytes]
+  __shared__ uint64_t bar[2];
+  const int rowbytes = D * static_cast<int>(sizeof(T));
+  const int chunks = rowbytes >> 4;
+  // CTA = (centroid c, part p): the member rows of a centroid are cut into `parts` equal runs (cluster sizes are very
+  // unequal after a few Lloyd steps: one CTA per centroid leaves the largest cluster on the critical path); the
+  // partial sums go to `partial` and are combined in part order by combine_parts_kernel
+  const int c = blockIdx.x / parts, part = blockIdx.x - c * parts;
+  const int c0 = seg_off[c], c1 = seg_off[c + 1];
+  const int per = (c1 - c0 + parts - 1) / parts;
+  const int s0 = min(c1, c0 + part * per), s1 = min(c1, s0 + per);
+  const int nb = (s1 - s0 + R - 1) / R;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int b) {   // warp 0: batch b -> buffer b & 1
+    const int r0 = s0 + b * R;
+    const int cnt = min(R, s1 - r0);
+    uint8_t* buf = rows_sm + static_cast<size_t>(b & 1) * R * rowbytes;
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar[b & 1], static_cast<uint32_t>(cnt) * rowbytes);
+    __syncwarp();
+    for (int i = threadIdx.x; i < cnt; i += 32)
+      bulk_load_1d(buf + static_cast<size_t>(i) * rowbytes, x + static_cast<size_t>(perm[r0 + i]) * D, rowbytes, &bar[b & 1]);
+  };
+  if (threadIdx.x < 32 && nb > 0) issue(0);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  for (int b = 0; b < nb; ++b) {
+    if (threadIdx.x < 32 && b + 1 < nb) issue(b + 1);   // its buffer was released by the barrier that ended batch b - 1
+    mbar_wait(&bar[b & 1], (b >> 1) & 1);
+    const int cnt = min(R, s1 - (s0 + b * R));
+    const uint8_t* buf = rows_sm + static_cast<size_t>(b & 1) * R * rowbytes;
+    if (threadIdx.x < chunks) {
+      int i = 0;
+      for (; i + 4 <= cnt; i += 4) {
+        const uint4 a0 = *reinterpret_cast<const uint4*>(buf + static_cast<size_t>(i) * rowbytes + threadIdx.x * 16);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(buf + static_cast<size_t>(i + 1) * rowbytes + threadIdx.x * 16);
+        const uint4 a2 = *reinterpret_cast<const uint4*>(buf + static_cast<size_t>(i + 2) * rowbytes + threadIdx.x * 16);
+        const uint4 a3 = *reinterpret_cast<const uint4*>(buf + static_cast<size_t>(i + 3) * rowbytes + threadIdx.x * 16);
+        add_row<T>(acc, a0); add_row<T>(acc, a1); add_row<T>(acc, a2); add_row<T>(acc, a3);
+      }
+      for (; i < cnt; ++i)
+        add_row<T>(acc, *reinterpret_cast<const uint4*>(buf + static_cast<size_t>(i) * rowbytes + threadIdx.x * 16));
+    }
+    __syncthreads();
+  }
+  float* out = parts > 1 ? partial + static_cast<size_t>(blockIdx.x) * D : packed + static_cast<size_t>(c) * (D + 1);
+  if (threadIdx.x < chunks) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) out[threadIdx.x * V + i] = acc[i];
+  }
+  if (parts == 1 && threadIdx.x == 0) out[D] = static_cast<float>(c1 - c0);
+}
+
+// packed[c][d] = sum over the parts (in order) of partial[c][part][d]; packed[c][D] = member count
+__global__ void __launch_bounds__(256) combine_parts_kernel(const float* __restrict__ partial,
+                                                            const int32_t* __restrict__ seg_off, int D, int parts,
+                                                            float* __restrict__ packed) {
+  const int c = blockIdx.x;
+  const float* in = partial + static_cast<size_t>(c) * parts * D;
+  float* out = packed + static_cast<size_t>(c) * (D + 1);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v = in[d];
+    for (int p = 1; p < parts; ++p) v += in[static_cast<size_t>(p) * D + d];
+    out[d] = v;
+  }
+  if (threadIdx.x == 0) out[D] = static_cast<float>(seg_off[c + 1] - seg_off[c]);
 }
 
 template <typename T>
@@ -426,7 +553,7 @@ extern "C" int msvit_gkm_assign(const void* x, int x_dtype, const void* centroid
 extern "C" size_t msvit_gkm_workspace_bytes(int64_t n, int k) {
   using namespace msvit::gkm;
   if (n < 0 || k <= 0) return 0;
-  return static_cast<size_t>(sort_blocks(n) > 0 ? sort_blocks(n) : 1) * k * sizeof(int32_t);
+  return (static_cast<size_t>(sort_blocks(n) > 0 ? sort_blocks(n) : 1) + 1) * k * sizeof(int32_t);   // histograms + label totals
 }
 
 extern "C" int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* perm, int32_t* seg_off, void* workspace,
@@ -441,13 +568,21 @@ extern "C" int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* 
   const int nb = sort_blocks(n);
   const size_t smem = static_cast<size_t>(k) * sizeof(int32_t);
   if (nb > 0) hist_kernel<<<nb, 128, smem, stream>>>(labels, static_cast<int>(n), k, hist);
-  scan_kernel<<<1, 256, 0, stream>>>(hist, nb, k, seg_off);
+  int32_t* tot = hist + static_cast<size_t>(nb > 0 ? nb : 1) * k;
+  block_offsets_kernel<<<ceil_div(k, 64), 64, 0, stream>>>(hist, nb, k, tot);
+  label_scan_kernel<<<1, 1024, 0, stream>>>(tot, k, seg_off);
   if (nb > 0) scatter_kernel<<<nb, 32, smem, stream>>>(labels, static_cast<int>(n), k, hist, seg_off, perm);
   return cuda_status(cudaGetLastError());
 }
 
+extern "C" size_t msvit_gkm_accumulate_workspace_bytes(int k, int D) {
+  if (k <= 0 || D <= 0) return 0;
+  return static_cast<size_t>(k) * msvit::gkm::kAccParts * D * sizeof(float);
+}
+
 extern "C" int msvit_gkm_accumulate(const void* x, int x_dtype, const int32_t* perm, const int32_t* seg_off,
-                                    float* packed, int64_t n, int k, int D, msvit_stream_t stream_) {
+                                    float* packed, int64_t n, int k, int D, void* workspace, size_t workspace_bytes,
+                                    msvit_stream_t stream_) {
   using namespace msvit;
   using namespace msvit::gkm;
   if (!x || !perm || !seg_off || !packed) return MSVIT_ERR_NULL;
@@ -457,6 +592,31 @@ extern "C" int msvit_gkm_accumulate(const void* x, int x_dtype, const int32_t* p
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return MSVIT_ERR_ALIGN;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int cols = D / V;
+  if (cols <= 256) {
+    // rows fetched by bulk copies: two batches of R rows per CTA in shared memory (about 48 KB, four CTAs per SM)
+    const int rowbytes = cols * 16;
+    int R = 24576 / rowbytes;
+    R = R > 16 ? 16 : (R < 4 ? 4 : R);
+    const size_t smem = 2u * static_cast<size_t>(R) * rowbytes;
+    const int threads = round_up(cols < 32 ? 32 : cols, 32);
+    // with a workspace the rows of every centroid are cut into kAccParts runs (load balance), else one CTA per centroid
+    const int parts = (workspace && workspace_bytes >= msvit_gkm_accumulate_workspace_bytes(k, D)) ? kAccParts : 1;
+    float* partial = static_cast<float*>(workspace);
+    cudaError_t e;
+    if (x_dtype == MSVIT_F32) {
+      e = cudaFuncSetAttribute(accumulate_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_status(e);
+      accumulate_bulk_kernel<float><<<k * parts, threads, smem, stream>>>(static_cast<const float*>(x), perm, seg_off, D, R,
+                                                                          parts, packed, partial);
+    } else {
+      e = cudaFuncSetAttribute(accumulate_bulk_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_status(e);
+      accumulate_bulk_kernel<uint16_t><<<k * parts, threads, smem, stream>>>(static_cast<const uint16_t*>(x), perm, seg_off, D,
+                                                                             R, parts, packed, partial);
+    }
+    if (parts > 1) combine_parts_kernel<<<k, 256, 0, stream>>>(partial, seg_off, D, parts, packed);
+    return cuda_status(cudaGetLastError());
+  }
   const int RL = cols <= 128 ? 4 : (cols <= 256 ? 2 : 1);
   const int threads = RL * cols;
   const size_t smem = static_cast<size_t>(RL) * D * sizeof(float);

@@ -47,7 +47,9 @@ _SIGNATURES = {
     "msvit_gkm_assign": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_ptr]),
     "msvit_gkm_workspace_bytes": (ctypes.c_size_t, [_c_i64, _c_int]),
     "msvit_gkm_sort": (_c_int, [_c_ptr, _c_i64, _c_int, _c_ptr, _c_ptr, _c_ptr, ctypes.c_size_t, _c_ptr]),
-    "msvit_gkm_accumulate": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_ptr]),
+    "msvit_gkm_accumulate_workspace_bytes": (ctypes.c_size_t, [_c_int, _c_int]),
+    "msvit_gkm_accumulate": (_c_int, [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_int, _c_int, _c_ptr,
+                                      ctypes.c_size_t, _c_ptr]),
     "msvit_gkm_finalize": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr]),
     "msvit_attention_mask": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr]),
     "msvit_cluster_key_sums": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr]),

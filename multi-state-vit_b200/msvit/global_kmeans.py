@@ -82,7 +82,8 @@ class GlobalKMeansPlan:
             self.labels = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
             self.perm = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
             self.seg_off = torch.empty(self.k + 1, dtype=torch.int32, device=dev)
-            self.ws_bytes = int(self.lib.msvit_gkm_workspace_bytes(self.n, self.k))
+            self.acc_ws_bytes = int(self.lib.msvit_gkm_accumulate_workspace_bytes(self.k, self.D))
+            self.ws_bytes = max(int(self.lib.msvit_gkm_workspace_bytes(self.n, self.k)), self.acc_ws_bytes)
             self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
             self.packed = torch.empty(self.k, self.D + 1, dtype=torch.float32, device=dev)
             self.centroids = torch.empty(self.k, self.D, dtype=torch.float32, device=dev)
@@ -117,7 +118,7 @@ class GlobalKMeansPlan:
                                      self.ws_bytes, st), "msvit_gkm_sort")
             mark(2)
             check(lib.msvit_gkm_accumulate(p(x), self.code, p(self.perm), p(self.seg_off), p(self.packed), self.n,
-                                           self.k, self.D, st), "msvit_gkm_accumulate")
+                                           self.k, self.D, p(self.ws), self.ws_bytes, st), "msvit_gkm_accumulate")
             mark(3)
         return self.packed
 

@@ -59,9 +59,12 @@ def test_argument_checks_fire_before_any_cuda_call(lib):
     assert lib.msvit_gkm_assign(p16, 5, p16, p16, None, 8, 2, 8, None) == -4
     assert lib.msvit_gkm_sort(p16, 8, 2, p16, p16, p16, 0, None) == -5                 # workspace too small
     assert lib.msvit_gkm_sort(p16, 8, 2, p16, p16, None, 64, None) == -1
-    assert lib.msvit_gkm_accumulate(p16, 1, p16, p16, p16, 8, 2, 12, None) == -2       # D % 8 for bf16
+    assert lib.msvit_gkm_accumulate(p16, 1, p16, p16, p16, 8, 2, 12, None, 0, None) == -2       # D % 8 for bf16
     assert lib.msvit_gkm_finalize(p16, None, None, 0, 2, 8, None) == -1
-    assert lib.msvit_gkm_workspace_bytes(4096, 10) == 2 * 10 * 4
+    assert lib.msvit_gkm_workspace_bytes(4096, 10) == (2 + 1) * 10 * 4   # two block histograms + the label totals
+    assert lib.msvit_ncut_fused(p16, 0, p16, p16, p16, p16, p16, 8 * 300, 8, 300, 64, 0, 3.0, 1.0, 16, 10, 1e-5, 0.0, 0, None) == -2  # N > 208
+    assert lib.msvit_ncut_fused(p16, 0, p16, p16, p16, p16, p16, 8 * 64, 8, 64, 64, 0, 3.0, 1.0, 24, 10, 1e-5, 0.0, 0, None) == -2   # block != 16
+    assert lib.msvit_discretise(p16, p16, None, None, p16, p16, None, 8, 1, 8, 4, 2, 0.1, 10, 7, None, None) == -4                  # method
     assert lib.msvit_gkm_assign(p16, 0, p16, p16, None, 0, 2, 8, None) == 0
     assert lib.msvit_attention_mask(None, p16, 1, 8, 2, None) == -1
     assert lib.msvit_attention_mask(p16, p16, 1, 0, 2, None) == -2
