@@ -212,3 +212,46 @@ def test_update_step_is_exact_and_keeps_empty_centres():
         torch.testing.assert_close(plan.centroids[7].cpu(), init[7])
         nz = cnt > 0
         torch.testing.assert_close(plan.centroids[nz].cpu().double(), sums[nz] / cnt[nz, None], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_c5_full_size_sampled_parity():
+    """BASELINE.json configs[4] at full size (1 000 000 x 768 bf16 rows, k = 1000), one Lloyd step: the assignment of a
+    random sample of rows equals the fp32 argmin over the same bf16 operands, the member counts are exact, and the
+    centroid sums of sampled centroids match a torch reduction of their member rows."""
+    import msvit
+    from msvit.global_kmeans import GlobalKMeansPlan
+    dev = "cuda:0"
+    n, D, k = 1_000_000, 768, 1000
+    g = torch.Generator(device=dev).manual_seed(1212)
+    centres = torch.randn(k, D, generator=g, device=dev)
+    x = torch.empty(n, D, dtype=torch.bfloat16, device=dev)
+    for r0 in range(0, n, 1 << 16):
+        r1 = min(n, r0 + (1 << 16))
+        lab = torch.randint(0, k, (r1 - r0,), generator=g, device=dev)
+        x[r0:r1] = (centres[lab] + 0.5 * torch.randn(r1 - r0, D, generator=g, device=dev)).bfloat16()
+    plan = GlobalKMeansPlan(n, D, k, torch.bfloat16, dev)
+    plan.set_centroids(x[:k].float())
+    packed = plan.local_step(x).clone()
+    torch.cuda.synchronize()
+    labels = plan.labels[:n].long()
+    cop = plan.centroids_op.float()                        # the bf16 operand the tensor cores read
+    idx = torch.randint(0, n, (8192,), generator=g, device=dev)
+    xs = x[idx].float()
+    score = (cop * cop).sum(1)[None, :] - 2.0 * xs @ cop.T
+    best = score.min(dim=1)
+    got = score.gather(1, labels[idx][:, None])[:, 0]
+    # the chosen centre attains the minimal score (ties / last-ulp differences allowed, a different centre is not)
+    assert torch.all(got <= best.values + 1e-3 * best.values.abs().clamp_min(1.0))
+    assert float((labels[idx] == best.indices).float().mean()) > 0.999
+    counts = torch.bincount(labels, minlength=k)
+    assert torch.equal(packed[:, D].round().long(), counts) and int(counts.sum()) == n
+    for c in torch.randint(0, k, (12,), generator=g, device=dev).tolist():
+        members = x[labels == c].float()
+        torch.testing.assert_close(packed[c, :D], members.sum(0), rtol=2e-4, atol=2e-2)
+    # perm is a stable sort by label: row ids ascending inside every label
+    perm, seg = plan.perm[:n].long(), plan.seg_off.long()
+    assert torch.equal(torch.sort(perm).values, torch.arange(n, device=dev))
+    c = int(torch.argmax(counts))
+    run = perm[seg[c]:seg[c + 1]]
+    assert torch.all(labels[run] == c) and torch.all(run[1:] > run[:-1])

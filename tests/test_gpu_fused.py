@@ -198,3 +198,59 @@ def test_axis_aligned_discretisation_matches_oracle(fused):
         c3, _, _, n3 = O.cluster_tokens(O.round_to_tf32(x2).double(), parent, ncut_dim=4, n_clusters=3,
                                         scale=default_scale(96), discretise="axis_align")
         assert o3.n_child.cpu().tolist() == n3.tolist() and torch.equal(o3.labels.cpu(), c3)
+
+
+def _planted_hierarchy(B, N, D, branching=4, levels=3, seed=99):
+    """Tokens of a 3-level planted hierarchy (4 x 4 x 4 leaves): centre = c1[a] + c2[a,b] / 2 + c3[a,b,c] / 4 + noise.
+    Returns x [B, N, D] and the leaf path (a, b, c) of every token."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.empty(B, N, D)
+    path = torch.empty(B, N, levels, dtype=torch.long)
+    for b in range(B):
+        c1 = torch.randn(branching, D, generator=g)
+        c2 = torch.randn(branching, branching, D, generator=g) * 0.5
+        c3 = torch.randn(branching, branching, branching, D, generator=g) * 0.25
+        leaf = torch.arange(N) % (branching ** levels)
+        leaf = leaf[torch.randperm(N, generator=g)]
+        a, bb, c = leaf // 16, (leaf // 4) % 4, leaf % 4
+        x[b] = c1[a] + c2[a, bb] + c3[a, bb, c] + 0.05 * torch.randn(N, D, generator=g)
+        path[b] = torch.stack([a, bb, c], dim=1)
+    return x, path
+
+
+def test_full_size_c4_three_hierarchical_levels():
+    """BASELINE.json configs[3] at config size (B=256 images of 1024 tokens, d=768, three levels of re-clustering, each
+    parent segment split into 4 children): the planted hierarchy is recovered on EVERY image, the caller contract
+    (children of a parent contiguous and ordered, msvitencoder.py:491-499) holds, and two sampled images agree with
+    the CPU oracle level by level."""
+    B, N, D = 256, 1024, 768
+    x, path = _planted_hierarchy(B, N, D)
+    xd = x.to(DEV)
+    scales = [default_scale(D), default_scale(D) / 4, default_scale(D) / 16]   # every level zooms in
+    sample = [0, 171]
+    xq = O.round_to_tf32(x[sample]).double()
+    parent_gpu, parent_cpu = None, None
+    for level in range(3):
+        out = msvit.cluster_tokens(xd, parent_gpu, ncut_dim=4, n_clusters=4, scale=scales[level],
+                                   n_parents=None if parent_gpu is None else 4 ** level, want_pool=(level == 2), pool_k=64)
+        assert bool(out.converged.all()), f"level {level}: eigensolver hit the cap"
+        labels = out.labels.cpu()
+        # planted partition of this level recovered on every image
+        want_key = sum(path[:, :, l] * (4 ** (level - l)) for l in range(level + 1))
+        for b in range(B):
+            assert torch.equal(O.canonical_relabel(labels[b])[0], O.canonical_relabel(want_key[b])[0]), (level, b)
+        assert int(labels.max()) + 1 == 4 ** (level + 1)
+        if parent_gpu is not None:
+            # children of parent p occupy a contiguous id range, ranges ordered by p: cumsum + searchsorted recovers it
+            nchild = out.n_child.cpu().long()
+            for b in (0, 77, 255):
+                cum = torch.cumsum(nchild[b], 0)
+                poc = torch.searchsorted(cum, torch.arange(int(labels[b].max()) + 1), side="right")
+                assert torch.equal(poc[labels[b]], parent_gpu[b].cpu())
+        child, _, _, nc = O.cluster_tokens(xq, parent_cpu, ncut_dim=4, n_clusters=4, scale=scales[level])
+        assert torch.equal(labels[sample], child), f"level {level}: sampled images differ from the oracle"
+        parent_gpu, parent_cpu = out.labels, child
+    assert int(out.counts.sum()) == B * N
+    pooled_ref, counts_ref = O.pool(x[sample].double(), child, 64)
+    assert torch.equal(out.counts[sample].cpu(), counts_ref)
+    torch.testing.assert_close(out.pooled[sample].cpu().double(), pooled_ref, rtol=1e-3, atol=1e-5)
