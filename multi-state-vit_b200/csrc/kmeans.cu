@@ -539,7 +539,8 @@ extern "C" int msvit_discretise(const float* V, const float* lam, const float* w
   if (!V || !labels || !n_child) return MSVIT_ERR_NULL;
   if (n_clusters <= 0 && !lam) return MSVIT_ERR_NULL;
   if (S < 0 || N <= 0 || ldv <= 0 || total_rows < 0 || max_iter <= 0) return MSVIT_ERR_SHAPE;
-  if (n_clusters > kMaxK || n_clusters > ldv || (n_clusters <= 0 && ldv > kMaxK)) return MSVIT_ERR_SHAPE;
+  // (ldv may exceed the cluster bound: with the eigenvalue threshold K = min(#{lam > thr}, kMaxK, n))
+  if (n_clusters > kMaxK || n_clusters > ldv || ldv > 128) return MSVIT_ERR_SHAPE;
   if (method != MSVIT_DISC_KMEANS && method != MSVIT_DISC_AXIS_ALIGN) return MSVIT_ERR_MODE;
   if (method == MSVIT_DISC_AXIS_ALIGN && (n_clusters > kKwayMaxK || (n_clusters <= 0 && ldv > kKwayMaxK) || init || centres))
     return MSVIT_ERR_SHAPE;
@@ -549,7 +550,8 @@ extern "C" int msvit_discretise(const float* V, const float* lam, const float* w
   P.discretise = method;
   P.V = V; P.lam = lam; P.weight = weight; P.init = init; P.labels = labels; P.n_child = n_child;
   P.centres = centres; P.seg_off = seg_off;
-  P.S = S; P.N = N; P.ldv = ldv; P.n_clusters = n_clusters; P.Kmax = n_clusters > 0 ? n_clusters : ldv;
+  P.S = S; P.N = N; P.ldv = ldv; P.n_clusters = n_clusters;
+  P.Kmax = n_clusters > 0 ? n_clusters : (ldv < kMaxK ? ldv : kMaxK);
   P.max_iter = max_iter; P.thr = eig_threshold;
   P.U = nullptr; P.H = nullptr; P.info = nullptr; P.Vout = nullptr; P.lam_out = nullptr; P.child = nullptr;
   P.m = 0; P.kconv = 0;

@@ -42,13 +42,48 @@ def fused_eligible(N: int, k: int, n_parents: int = 1) -> bool:
     return n_parents == 1 and k + 4 <= FUSED_BLOCK and FUSED_BLOCK < N and ((N + 15) & ~15) <= FUSED_MAX_TOKENS
 
 
+MAX_DENSE_EIG = 128  # ncut_dim served by the dense solver
+
+
 def default_block(k: int, oversample: int = 8) -> int:
-    """Subspace width: k wanted + oversampling, multiple of 4, at most MAX_EIG_BLOCK."""
+    """Subspace width of the iterative solvers: k wanted + oversampling, multiple of 4, at most MAX_EIG_BLOCK.
+    Returns 0 when k does not fit (ncut_dim > MAX_EIG_BLOCK): such requests go to the dense solver."""
+    if k > _lib.MAX_EIG_BLOCK:
+        if k > MAX_DENSE_EIG:
+            raise ValueError(f"ncut_dim={k} exceeds the supported maximum {MAX_DENSE_EIG}")
+        return 0
     m = (k + oversample + 3) & ~3
     m = min(m, _lib.MAX_EIG_BLOCK)
-    if m < k:
-        raise ValueError(f"ncut_dim={k} exceeds the supported subspace width {_lib.MAX_EIG_BLOCK}")
     return max(m, (k + 3) & ~3)
+
+
+def dense_ncut_eig(A: torch.Tensor, deg: torch.Tensor, k: int):
+    """All-eigenpairs solve for large ncut_dim (33 .. 128; the author's logs use 100 on 784 tokens,
+    logging/10-03-2024/run_log.png, sandbox/test.py:66): A [S, N, lda] fp32 as written by the affinity kernel,
+    deg [S, N] -> (V [S, N, k], lam [S, k]), eigenvalues descending, canonical sign.
+
+    A block subspace iteration converges hopelessly slowly that deep inside the spectrum, so this path does what the
+    reference's closed form does (sandbox/test.py:114-118): a full symmetric eigendecomposition of D^-1/2 A D^-1/2.
+    It is a LIBRARY call (cuSOLVER through torch.linalg.eigh on the GPU), not one of this repository's kernels; it
+    allocates and may synchronise, so plans that use it cannot be captured in a CUDA graph."""
+    S, N = deg.shape
+    r = torch.rsqrt(deg)
+    Abar = A[:, :, :N] * r[:, :, None] * r[:, None, :]
+    Abar = 0.5 * (Abar + Abar.transpose(1, 2))
+    w, U = torch.linalg.eigh(Abar)
+    kk = min(k, N)
+    lam = torch.zeros(S, k, dtype=torch.float32, device=A.device)
+    V = torch.zeros(S, N, k, dtype=torch.float32, device=A.device)
+    lam[:, :kk] = w.flip(-1)[:, :kk]
+    Vk = U.flip(-1)[:, :, :kk]
+    # largest-|entry| of every column positive, ties -> lowest row
+    av = Vk.abs()
+    mx = av.max(dim=1, keepdim=True).values
+    first = (av >= mx).to(torch.int8).argmax(dim=1)                       # first maximal row
+    sgn = torch.sign(torch.gather(Vk, 1, first[:, None, :]))
+    sgn = torch.where(sgn == 0, torch.ones_like(sgn), sgn)
+    V[:, :, :kk] = Vk * sgn
+    return V, lam
 
 
 class ClusterPlan:
@@ -85,6 +120,7 @@ class ClusterPlan:
         self.dtype_code = _lib.F32 if dtype == torch.float32 else _lib.BF16
         self.k = int(ncut_dim)
         self.block = default_block(self.k, oversample)
+        self.dense = self.block == 0   # ncut_dim > 32: dense (library) eigendecomposition
         self.mode = _lib.DIST[mode]
         self.gamma = float(gamma)
         self.scale = float(D) if scale is None else float(scale)
@@ -97,10 +133,12 @@ class ClusterPlan:
         self.n_converge = min(self.nk, self.k) if self.nk > 0 else 0
         self.kmeans_iters, self.eig_iters, self.eig_tol = int(kmeans_iters), int(eig_iters), float(eig_tol)
         self.want_pool = bool(want_pool)
-        self.Kp = int(pool_k) if pool_k is not None else self.P * (self.nk if self.nk > 0 else self.k)
+        self.Kp = int(pool_k) if pool_k is not None else self.P * (self.nk if self.nk > 0 else min(self.k, _lib.MAX_EIG_BLOCK))
         B, N, D, P, k = self.B, self.N, self.D, self.P, self.k
         self.S = B * P
         # whole images of up to 224 tokens take the fused kernel: the affinity stays in tensor memory
+        if self.dense and int(n_parents) != 1:
+            raise NotImplementedError("ncut_dim > 32 is served by the dense solver, which takes whole images only")
         can_fuse = fused_eligible(N, self.k, P)
         if fused and not can_fuse:
             raise ValueError("the fused kernel needs whole images (one parent), 16 < tokens <= 208 and ncut_dim <= 12")
@@ -187,9 +225,15 @@ class ClusterPlan:
                                                 self.gamma, self.scale, p(self.seg_off), p(self.a_off), st),
                       "msvit_affinity_degree")
                 mark(2)
-                check(lib.msvit_ncut_eig(p(self.A), p(self.deg), p(self.V), p(self.lam), p(self.iters), rows, S, N, k,
-                                         self.block, self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge,
-                                         p(self.seg_off), p(self.a_off), st), "msvit_ncut_eig")
+                if self.dense:
+                    Vd, lamd = dense_ncut_eig(self.A.view(B, N, ops.lda_of(N)), self.deg.view(B, N), k)
+                    self.V.copy_(Vd.view(rows, k))
+                    self.lam.copy_(lamd)
+                    self.iters.fill_(1)
+                else:
+                    check(lib.msvit_ncut_eig(p(self.A), p(self.deg), p(self.V), p(self.lam), p(self.iters), rows, S, N, k,
+                                             self.block, self.eig_iters, self.eig_tol, self.lam_floor, self.n_converge,
+                                             p(self.seg_off), p(self.a_off), st), "msvit_ncut_eig")
                 mark(3)
                 check(lib.msvit_discretise(p(self.V), p(self.lam), p(self.deg), None, p(self.labels_sorted),
                                            p(self.n_child), None, rows, S, N, k, self.nk, self.thr, self.kmeans_iters,
@@ -273,6 +317,9 @@ def ncut_eig(A: torch.Tensor, deg: torch.Tensor, k: int, *, max_iter: int = 60, 
     B, N, lda = A.shape
     if lda != ops.lda_of(N):
         raise ValueError("A must be [B, N, (N+3)&~3]")
+    if default_block(int(k), oversample) == 0:
+        V, lam = dense_ncut_eig(A.contiguous(), deg.contiguous(), int(k))
+        return V, lam, torch.ones(B, dtype=torch.int32, device=A.device)
     V, lam, iters = ops.ncut_eig(A.contiguous().view(-1), deg.contiguous().view(-1), B, N, int(k),
                                  default_block(int(k), oversample), int(max_iter), float(tol), float(lam_floor),
                                  int(n_converge), None, None)

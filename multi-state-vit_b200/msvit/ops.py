@@ -100,7 +100,7 @@ def kmeans(V: torch.Tensor, lam: Optional[torch.Tensor], weight: Optional[torch.
     """-> (labels [rows] int32 local canonical ids, n_child [S] int32, centres [S, Kmax, Kmax])."""
     _need_cuda(V, lam, weight, init, seg_off)
     rows, ldv = V.shape
-    Kmax = n_clusters if n_clusters > 0 else ldv
+    Kmax = n_clusters if n_clusters > 0 else min(ldv, _lib.MAX_EIG_BLOCK)
     with torch.cuda.device(V.device):
         labels = torch.empty(rows, dtype=torch.int32, device=V.device)
         n_child = torch.empty(S, dtype=torch.int32, device=V.device)
@@ -115,7 +115,7 @@ def kmeans(V: torch.Tensor, lam: Optional[torch.Tensor], weight: Optional[torch.
 @kmeans.register_fake
 def _(V, lam, weight, init, S, N, n_clusters, eig_threshold, max_iter, seg_off):
     rows, ldv = V.shape
-    Kmax = n_clusters if n_clusters > 0 else ldv
+    Kmax = n_clusters if n_clusters > 0 else min(ldv, _lib.MAX_EIG_BLOCK)
     return (V.new_empty(rows, dtype=torch.int32), V.new_empty(S, dtype=torch.int32), V.new_empty(S, Kmax, Kmax))
 
 

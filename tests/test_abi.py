@@ -104,5 +104,6 @@ def test_block_width_rule():
     from msvit.functional import default_block
     assert default_block(8) == 16 and default_block(16) == 24 and default_block(2) == 12
     assert default_block(30) == 32 and default_block(32) == 32
+    assert default_block(33) == 0 and default_block(100) == 0     # dense solver (ncut_dim up to 128)
     with pytest.raises(ValueError):
-        default_block(33)
+        default_block(129)

@@ -254,3 +254,18 @@ def test_full_size_c4_three_hierarchical_levels():
     pooled_ref, counts_ref = O.pool(x[sample].double(), child, 64)
     assert torch.equal(out.counts[sample].cpu(), counts_ref)
     torch.testing.assert_close(out.pooled[sample].cpu().double(), pooled_ref, rtol=1e-3, atol=1e-5)
+
+
+def test_large_ncut_dim_takes_the_dense_solver():
+    """ncut_dim = 100 on 784 tokens (the author's configuration: sandbox/test.py:22,47-52,66 and the run log): served by
+    the dense eigendecomposition; eigenvalues / eigenvectors match exact eigh, the eigenvalue threshold picks the number of
+    children, labels match the oracle."""
+    B, N, D, K = 2, 784, 768, 12
+    x, _ = planted_tokens(B, N, D, K)
+    out = msvit.cluster_tokens(x.to(DEV), ncut_dim=100, eigenvalue_threshold=0.05, scale=default_scale(D))
+    assert out.eigvecs.shape == (B, N, 100) and out.eigvals.shape == (B, 1, 100)
+    child, eigvecs, eigvals, nc = O.cluster_tokens(O.round_to_tf32(x).double(), None, ncut_dim=100, eigenvalue_threshold=0.05,
+                                                   scale=default_scale(D))
+    np.testing.assert_allclose(out.eigvals[:, 0].cpu().numpy(), eigvals[:, 0].numpy(), rtol=RTOL, atol=2e-6)
+    assert out.n_child.cpu().tolist() == nc.tolist()
+    assert torch.equal(out.labels.cpu(), child)

@@ -109,7 +109,8 @@ def test_kmeans_edge_cases():
 
 
 # ----------------------------------------------------------------------------------------- eigensolver
-@pytest.mark.parametrize("case", [(196, 768, 8, 8), (64, 32, 3, 4), (10, 16, 2, 8), (576, 1024, 16, 16)])
+@pytest.mark.parametrize("case", [(196, 768, 8, 8), (64, 32, 3, 4), (10, 16, 2, 8), (576, 1024, 16, 16),
+                                  (784, 768, 12, 100)])   # the last one: the author's shape (sandbox/test.py:22,47-52,66)
 def test_ncut_eig_matches_exact_eigh(case):
     N, D, Kp, k = case
     B = 3
