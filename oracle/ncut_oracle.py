@@ -283,6 +283,40 @@ def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = Non
     return child, eigvecs, eigvals, n_children
 
 
+# --------------------------------------------------------------------------- flattened-batch Nystrom NCut
+def nystrom_ncut(x: torch.Tensor, k: int, sample_idx: torch.Tensor, knn: int = 10, mode: str = "rbf", gamma: float = 3.0,
+                 scale: Optional[float] = None):
+    """Restates the sample -> exact NCut -> kNN propagation scheme of ncut_pytorch.NCUT.fit_transform for inputs larger
+    than `num_sample` (call sites model/clustering/modeling_spectral.py:254-256, modeling_fps.py:36-37).  UNPINNED: the
+    package is absent; this mirrors multi-state-vit_b200/msvit/nystrom.py step by step in fp64 with exact eigh.
+    x [n, D], sample_idx sorted row ids -> (eigvecs [n, k], eigvals [k])."""
+    n, D = x.shape
+    xs = x[sample_idx]
+    A = affinity(xs, mode, gamma, scale)
+    Vs, lam, _ = ncut_eig(A, k)
+    if sample_idx.numel() == n:
+        return Vs, lam
+    out = x.new_zeros(n, k)
+    out[sample_idx] = Vs
+    rest = torch.ones(n, dtype=torch.bool)
+    rest[sample_idx] = False
+    ridx = torch.nonzero(rest).flatten()
+    s = float(D) if scale is None else float(scale)
+    xr = x[ridx]
+    g = xr @ xs.T
+    if mode == "cosine":
+        d = 1.0 - g * torch.rsqrt((xr * xr).sum(-1))[:, None] * torch.rsqrt((xs * xs).sum(-1))[None, :]
+    elif mode == "rbf":
+        d = (0.5 * ((xr * xr).sum(-1)[:, None] + (xs * xs).sum(-1)[None, :]) - g) / s
+    else:
+        d = (xr.norm(dim=-1)[:, None] * xs.norm(dim=-1)[None, :] - g) / s
+    a = torch.exp(-torch.clamp_min(d, 0.0) / gamma)
+    w, nb = torch.topk(a, min(knn, xs.shape[0]), dim=1)
+    w = w / w.sum(dim=1, keepdim=True)
+    out[ridx] = (w[:, :, None] * Vs[nb]).sum(dim=1)
+    return out, lam
+
+
 # --------------------------------------------------------------------------- dataset-level k-means
 def global_kmeans(feats: torch.Tensor, k: int, iters: int, init: Optional[torch.Tensor] = None):
     """DeepCluster-style Lloyd over all rows (modeling_spectral.py:254-256 flattened batch).

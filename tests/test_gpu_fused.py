@@ -269,3 +269,28 @@ def test_large_ncut_dim_takes_the_dense_solver():
     np.testing.assert_allclose(out.eigvals[:, 0].cpu().numpy(), eigvals[:, 0].numpy(), rtol=RTOL, atol=2e-6)
     assert out.n_child.cpu().tolist() == nc.tolist()
     assert torch.equal(out.labels.cpu(), child)
+
+
+def test_flattened_batch_nystrom_ncut_matches_oracle():
+    """SURVEY 8(f).4 (modeling_spectral.py:254-256): NCut over all B*N tokens at once with sampling + kNN propagation.
+    Same sampled rows on both sides (seeded CPU permutation); per-column agreement up to the eigen-gap, and the
+    per-image k-means on the shared embedding recovers a batch-level planted partition."""
+    from msvit.nystrom import nystrom_ncut, flattened_batch_cluster, sample_rows
+    B, N, D, K = 12, 196, 128, 5
+    g = torch.Generator().manual_seed(3)
+    centres = torch.randn(K, D, generator=g)
+    lab = torch.randint(0, K, (B, N), generator=g)
+    x = centres[lab] + 0.4 * torch.randn(B, N, D, generator=g)            # the SAME K classes in every image
+    flat = x.reshape(B * N, D)
+    s = default_scale(D)
+    # (a) every row sampled: exact dense NCut on 2352 rows (the torch block iteration: sample > 1024 rows)
+    # (b) 600 sampled rows: native per-segment kernels on the sample + propagation
+    for ns in (B * N, 600):
+        V, lam, idx = nystrom_ncut(flat.to(DEV), K, num_sample=ns, scale=s, seed=11)
+        assert torch.equal(idx.cpu(), sample_rows(B * N, ns, 11))
+        Vref, lref = O.nystrom_ncut(O.round_to_tf32(flat).double(), K, idx.cpu(), scale=s)
+        np.testing.assert_allclose(lam.cpu().numpy(), lref.numpy(), rtol=RTOL, atol=1e-6)
+        assert O.subspace_distance(V.cpu().double(), Vref) < 2e-2
+        labels, Vb, _ = flattened_batch_cluster(x.to(DEV), K, K, num_sample=ns, scale=s, seed=11)
+        for b in range(B):
+            assert torch.equal(labels[b].cpu(), O.canonical_relabel(lab[b])[0]), (ns, b)
