@@ -187,7 +187,7 @@ int msvit_attention_mask(const int64_t* cluster_indices, uint8_t* mask, int B, i
 /* Cluster-compressed attention statistics: the transmitter sums of compress_tokens_with_cluster_indices
  * (model/multistate_encoder/modeling_msvitencoder.py:182-186):
  *   out[b, h, q, c] = sum over the keys k of cluster c of attn[b, h, q, k].
- * attn [B, H, N, N] fp32 (16-byte aligned), cluster_indices [B, N] int64, out [B, H, N, C] fp32, C <= 32.
+ * attn [B, H, N, N] fp32 (16-byte aligned), cluster_indices [B, N] int64, out [B, H, N, C] fp32, C <= 64.
  * The receiver means of the same function (:187-190) are msvit_pool on the [B*H, N, N] view of attn. */
 int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_indices, float* out, int B, int H, int N, int C,
                            msvit_stream_t stream);

@@ -28,7 +28,7 @@ __device__ __forceinline__ uint32_t predicate(int q, int k, int C2, int nb, cons
 
 __global__ void __launch_bounds__(256) attention_mask_kernel(const int64_t* __restrict__ cluster_indices,
                                                              uint8_t* __restrict__ mask, int N, int C) {
-  extern __shared__ int lab[];  // [N] labels of this image, then one int for the cluster count
+  extern __shared__ int lab[];  // [N] labels of this image
   __shared__ int wmax[8];
   const int b = blockIdx.y;
   const int C2 = 2 * C, L = C2 + N;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) key_sums_kernel(const float* __restrict__
     float* o = out + (static_cast<size_t>(bh) * N + q) * C;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
-      if (lane == (c & 31) && c < C) o[c] = acc[c];
+      if (lane == (c & 31) && c < C) o[c] = acc[c];   // (lane l writes clusters l, l + 32)
   }
 }
 
@@ -156,7 +156,7 @@ extern "C" int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_
                                       int C, msvit_stream_t stream_) {
   using namespace msvit;
   if (!attn || !cluster_indices || !out) return MSVIT_ERR_NULL;
-  if (B < 0 || H <= 0 || N <= 0 || C <= 0 || C > 32 || N > 8192 || static_cast<long long>(B) * H > 65535) return MSVIT_ERR_SHAPE;
+  if (B < 0 || H <= 0 || N <= 0 || C <= 0 || C > 64 || N > 8192 || static_cast<long long>(B) * H > 65535) return MSVIT_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(attn) & 15) != 0) return MSVIT_ERR_ALIGN;
   if (B == 0) return MSVIT_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -165,6 +165,7 @@ extern "C" int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_
   const size_t smem = static_cast<size_t>((N + 3) & ~3) * sizeof(int);
   if (C <= 8) mask::key_sums_kernel<8><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
   else if (C <= 16) mask::key_sums_kernel<16><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
-  else mask::key_sums_kernel<32><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
+  else if (C <= 32) mask::key_sums_kernel<32><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
+  else mask::key_sums_kernel<64><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
   return cuda_status(cudaGetLastError());
 }

@@ -373,7 +373,9 @@ def cluster_attention_stats(attention_probs: torch.Tensor, cluster_indices: torc
         transmitter [B, H, N, C] = sum of attention_probs[b, h, q, :] over the KEYS of each cluster
         receiver    [B, H, C, N] = mean of attention_probs[b, h, :, k] over the QUERIES of each cluster (empty -> 0)
 
-    attention_probs [B, H, N, N] fp32, cluster_indices [B, N] int64; the reference materialises a 5-D broadcast."""
+    attention_probs [B, H, N, N] fp32, cluster_indices [B, N] int64, n_clusters <= 64 (the author's logs show up to
+    39 clusters per image); the reference materialises a 5-D broadcast.  An empty cluster gives receiver rows of 0
+    where the reference's 0/0 gives NaN."""
     if attention_probs.dim() != 4 or attention_probs.shape[-1] != attention_probs.shape[-2]:
         raise ValueError("attention_probs must be [batch, heads, tokens, tokens]")
     if not attention_probs.is_cuda:

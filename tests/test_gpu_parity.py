@@ -327,7 +327,8 @@ def test_ncut_eig_partial_convergence_request():
         check_eigvecs(V[b], lref.tolist(), Vref, Kp)
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 196, 8), (1, 2, 50, 5), (2, 1, 33, 12), (1, 4, 256, 20)])
+@pytest.mark.parametrize("shape", [(2, 3, 196, 8), (1, 2, 50, 5), (2, 1, 33, 12), (1, 4, 256, 20), (1, 2, 784, 39),
+                                   (1, 1, 300, 64)])
 def test_cluster_attention_stats_match_reference_restatement(shape):
     # compress_tokens_with_cluster_indices (msvitencoder.py:182-190): transmitter sums and receiver means
     B, H, N, C = shape
