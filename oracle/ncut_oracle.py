@@ -1,11 +1,14 @@
 """CPU oracle for the token-grouping hot path (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
 
-    PARITY UNPINNED: the reference (JophiArcana/multi-state-ViT) holds no golden
-    vectors, tests or recorded outputs for this path, and the arithmetic lives in
-    third-party packages that are absent from /root/reference and from this image
-    (ncut-pytorch==1.7.9, cuml~=24.10, fast_pytorch_kmeans; requirements.txt:27,32).
-    This file restates the algorithm from the reference's own call sites and its
-    in-repo closed form; it defines parity for this repository.
+    PARITY: pinned where the reference is executable, unpinned where it is not.  Four pieces of the reference's own
+    plain-torch arithmetic are executed from the checkout by tests/golden/make_reference_fixtures.py and this file
+    reproduces them (tests/test_reference_fixtures.py): the attention mask (modeling_msvitencoder.py:426-467), the
+    transmitter / receiver attention statistics (:169,182-190), the closed-form NCut of sandbox/test.py:100,106-118
+    (normprod distance, exp, degree, normalised Laplacian, eigh -- to 1e-9) and the per-label mean centres /
+    nearest-centre assignment (modeling_spectral.py:125-127,129).  What stays UNPINNED is the third-party arithmetic
+    absent from /root/reference and from this image (ncut-pytorch==1.7.9, cuml~=24.10, fast_pytorch_kmeans;
+    requirements.txt:27,32): the solver / sampling / sign conventions of NCUT.fit_transform, cuML's k-means
+    initialisation and kway_ncut are restated from the call sites and the published algorithms.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this module.  The product path (multi-state-vit_b200/) never does.
