@@ -973,13 +973,75 @@ __device__ __forceinline__ void jacobi_impl(float* __restrict__ H, float* __rest
   }
 }
 
-// Small blocks (the leading block of the final Rayleigh-Ritz step) are diagonalised by warp 0 alone: no CTA
-// barrier per round, the other warps wait once.
+// Blocks of at most 8 x 8 (the leading block of the final Rayleigh-Ritz step) by ONE warp with no rotation exchange:
+// lane (a, t) = (lane / half, lane % half) owns the 2 x 2 block (pair a, pair t) of H (lanes below half^2) and the
+// row-a, pair-t slice of S, and computes the two rotations it needs itself from H's diagonal blocks -- a round is
+// load -> rotate -> __syncwarp -> store -> __syncwarp, about half the latency of the broadcast-through-shared form.
+template <class G>
+__device__ __forceinline__ void jacobi_warp8(float* H, float* Sm, int ld, int md, int max_sweeps) {
+  const int lane = G::tid() & 31;
+  for (int e = lane; e < md * md; e += 32) {
+    const int a = e / md, b = e - a * md;
+    Sm[a * ld + b] = a == b ? 1.f : 0.f;
+    if (a < b) {
+      const float v = 0.5f * (H[a * ld + b] + H[b * ld + a]);
+      H[a * ld + b] = v;
+      H[b * ld + a] = v;
+    }
+  }
+  __syncwarp();
+  const int half = md >> 1;
+  const int nb = half * half, ns = md * half;   // <= 16, <= 32
+  const int ta = lane / half, tb = lane - ta * half;
+  auto pair_of = [&](int t, int r, int& p, int& q) {
+    if (t == 0) { p = r; q = md - 1; }
+    else {
+      p = r + t; if (p >= md - 1) p -= md - 1;
+      q = r - t; if (q < 0) q += md - 1;
+    }
+    if (p > q) { const int x = p; p = q; q = x; }
+  };
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    bool big = false;
+    for (int r = 0; r < md - 1; ++r) {
+      int p1 = 0, q1 = 1, p2 = 0, q2 = 1;
+      float c1 = 1.f, s1 = 0.f, c2 = 1.f, s2 = 0.f;
+      float npp = 0.f, npq = 0.f, nqp = 0.f, nqq = 0.f, nsp = 0.f, nsq = 0.f;
+      if (lane < ns) {
+        pair_of(tb, r, p2, q2);
+        jacobi_rot(H[p2 * ld + p2], H[q2 * ld + q2], H[p2 * ld + q2], c2, s2, big);
+        const float sp = Sm[ta * ld + p2], sq = Sm[ta * ld + q2];
+        nsp = c2 * sp - s2 * sq;
+        nsq = s2 * sp + c2 * sq;
+      }
+      if (lane < nb) {
+        pair_of(ta, r, p1, q1);
+        bool unused = false;
+        jacobi_rot(H[p1 * ld + p1], H[q1 * ld + q1], H[p1 * ld + q1], c1, s1, unused);
+        const float hpp = H[p1 * ld + p2], hpq = H[p1 * ld + q2], hqp = H[q1 * ld + p2], hqq = H[q1 * ld + q2];
+        const float rpp = c1 * hpp - s1 * hqp, rpq = c1 * hpq - s1 * hqq;
+        const float rqp = s1 * hpp + c1 * hqp, rqq = s1 * hpq + c1 * hqq;
+        npp = c2 * rpp - s2 * rpq; npq = s2 * rpp + c2 * rpq;
+        nqp = c2 * rqp - s2 * rqq; nqq = s2 * rqp + c2 * rqq;
+        if (ta == tb) { npq = 0.f; nqp = 0.f; }
+      }
+      __syncwarp();
+      if (lane < ns) { Sm[ta * ld + p2] = nsp; Sm[ta * ld + q2] = nsq; }
+      if (lane < nb) {
+        H[p1 * ld + p2] = npp; H[p1 * ld + q2] = npq; H[q1 * ld + p2] = nqp; H[q1 * ld + q2] = nqq;
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, big)) break;
+  }
+}
+
+// Small blocks are diagonalised by warp 0 alone (no CTA barrier per round, the other warps wait once).
 template <class G>
 __device__ __forceinline__ void jacobi(float* __restrict__ H, float* __restrict__ Sm, int ld, int md, int max_sweeps,
                                        float* __restrict__ rot) {
   if (md <= 8) {
-    if (G::tid() < 32) jacobi_impl<true, G>(H, Sm, ld, md, max_sweeps, rot);
+    if (G::tid() < 32) jacobi_warp8<G>(H, Sm, ld, md, max_sweeps);
     G::sync();
   } else {
     jacobi_impl<false, G>(H, Sm, ld, md, max_sweeps, rot);

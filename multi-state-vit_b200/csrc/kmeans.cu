@@ -16,7 +16,24 @@ namespace msvit {
 namespace km {
 
 constexpr int kThreads = 128;
+
+#ifdef KM_PROFILE
+// Development instrumentation: cycles thread 0 of every CTA spends in each phase of ritz_kmeans_kernel.
+enum { KP_JACOBI, KP_ROTATE, KP_SEED, KP_LLOYD, KP_RELABEL, KP_COUNT };
+__device__ unsigned long long g_km_cycles[KP_COUNT];
+#define KPHASE_BEGIN() long long kp_t0 = clock64()
+#define KPHASE_END(ph)                                                                         \
+  do {                                                                                         \
+    const long long kp_t1 = clock64();                                                         \
+    if (threadIdx.x == 0) atomicAdd(&g_km_cycles[ph], (unsigned long long)(kp_t1 - kp_t0));    \
+    kp_t0 = kp_t1;                                                                             \
+  } while (0)
+#else
+#define KPHASE_BEGIN()
+#define KPHASE_END(ph)
+#endif
 constexpr int kMaxK = MSVIT_MAX_EIG_BLOCK;
+constexpr int kRitzTokens = 2;   // tokens a thread of ritz_kmeans_kernel keeps in registers: N <= 2 * kThreads
 
 struct Params {
   const float* V;
@@ -40,81 +57,130 @@ struct Params {
   int discretise;        // 0 = k-means, 1 = axis-aligned rotation (kway_ncut)
 };
 
-// block-wide argmax of (value, index) with ties -> lowest index; result broadcast to all threads
-__device__ __forceinline__ int block_argmax(float v, int idx, float* sval, int* sidx) {
+// block-wide argmax of (value, index) with ties -> lowest index; result returned to all threads.  One barrier per
+// call: every thread combines the per-warp winners itself, and consecutive calls alternate between the two halves
+// of sval / sidx (`flip`), so a call never overwrites what a slower thread is still reading.
+__device__ __forceinline__ int block_argmax(float v, int idx, float* sval, int* sidx, int& flip) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = kThreads / 32;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, v, o);
     const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
-  if (lane == 0) { sval[warp] = v; sidx[warp] = idx; }
+  float* sv = sval + flip * W;
+  int* si = sidx + flip * W;
+  flip ^= 1;
+  if (lane == 0) { sv[warp] = v; si[warp] = idx; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kThreads / 32; ++w)
-      if (sval[w] > v || (sval[w] == v && sidx[w] < idx)) { v = sval[w]; idx = sidx[w]; }
-    sidx[0] = idx;
+  v = sv[0]; idx = si[0];
+#pragma unroll
+  for (int w = 1; w < W; ++w) {
+    const float ov = sv[w];
+    const int oi = si[w];
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
-  __syncthreads();
-  const int r = sidx[0];
-  __syncthreads();
-  return r;
+  return idx;
 }
 
-// squared distance of point i (column i of the transposed embedding, row stride ldp) to centre c
-__device__ __forceinline__ float sqdist(const float* __restrict__ pt, int ldp, int i, const float* __restrict__ c, int K) {
-  float d = 0.f;
-  for (int j = 0; j < K; ++j) {
-    const float t = pt[j * ldp + i] - c[j];
-    d = fmaf(t, t, d);
-  }
-  return d;
+// Point i of the transposed embedding (row stride ldp) in registers, coordinates beyond K read as 0.
+template <int KP>
+__device__ __forceinline__ void load_point(const float* pts, int ldp, int i, int K, float (&p)[KP]) {
+#pragma unroll
+  for (int j = 0; j < KP; ++j) p[j] = j < K ? pts[j * ldp + i] : 0.f;
 }
 
-// Shared-memory arrays of one segment's k-means (carved from dynamic shared memory by both kernels).
+// squared distance of a register point to a centre row in shared memory (16-byte aligned, 0 beyond K)
+template <int KP>
+__device__ __forceinline__ float sqdist(const float (&p)[KP], const float* c) {
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; j += 4) {
+    const float4 cv = *reinterpret_cast<const float4*>(c + j);
+    const float t0 = p[j] - cv.x, t1 = p[j + 1] - cv.y, t2 = p[j + 2] - cv.z, t3 = p[j + 3] - cv.w;
+    d0 = fmaf(t0, t0, d0);
+    d1 = fmaf(t1, t1, d1);
+    d0 = fmaf(t2, t2, d0);
+    d1 = fmaf(t3, t3, d1);
+  }
+  return d0 + d1;
+}
+
+template <int KP>
+__device__ __forceinline__ float sqdist(const float (&p)[KP], const float (&c)[KP]) {
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; j += 2) {
+    const float t0 = p[j] - c[j], t1 = p[j + 1] - c[j + 1];
+    d0 = fmaf(t0, t0, d0);
+    d1 = fmaf(t1, t1, d1);
+  }
+  return d0 + d1;
+}
+
+// Shared-memory arrays of one segment's k-means (carved from dynamic shared memory by both kernels); every array
+// starts on a 16-byte boundary.
 struct Work {
-  float* cen;    // [kMaxK][kMaxK + 1]
-  float* mind;   // [N]
-  int* lab;      // [N]
+  float* cen;    // [kMaxK][LDC]   centres, 0 beyond the K leading coordinates
+  float* mind;   // [N4]
+  int* lab;      // [N4]           -1 beyond the segment's n points
   int* map;      // [kMaxK]
   float* part;   // [2][kMaxK * kMaxK] partial centre sums
   int* pcnt;     // [2][kMaxK] partial counts
   float* pts;    // [Kcap][ldp] transposed embedding
   int ldp;
-  float* sval;   // [kThreads / 32]
-  int* sidx;     // [kThreads / 32]
+  float* sval;   // [2][kThreads / 32]
+  int* sidx;     // [2][kThreads / 32]
   int* changed;  // [1]
 };
-constexpr int LDC = kMaxK + 1;
+constexpr int LDC = kMaxK + 4;   // 16-byte aligned centre rows (read as float4 broadcasts)
+
+// row stride of the transposed embedding: a multiple of 4 (float4 reads along the tokens) and = 4 mod 32 (the float4
+// reads of 8 coordinate rows at the same token fall in 32 distinct banks)
+__host__ __device__ __forceinline__ int pts_stride(int N) { return ((N + 31) & ~31) + 4; }
+
+static size_t work_bytes(int N, int kcap) {
+  const size_t N4 = (static_cast<size_t>(N) + 3) & ~static_cast<size_t>(3);
+  return sizeof(float) * (kMaxK * LDC + N4 + 2 * kMaxK * kMaxK + static_cast<size_t>(kcap) * pts_stride(N)) +
+         sizeof(int) * (N4 + kMaxK + 2 * kMaxK);
+}
 
 __device__ __forceinline__ Work carve(float* smem, int N, float* sval, int* sidx, int* changed) {
+  const int N4 = (N + 3) & ~3;
   Work w;
   w.cen = smem;
-  w.mind = w.cen + kMaxK * (kMaxK + 1);
-  w.lab = reinterpret_cast<int*>(w.mind + N);
-  w.map = w.lab + N;
+  w.mind = w.cen + kMaxK * LDC;
+  w.lab = reinterpret_cast<int*>(w.mind + N4);
+  w.map = w.lab + N4;
   w.part = reinterpret_cast<float*>(w.map + kMaxK);
   w.pcnt = reinterpret_cast<int*>(w.part + 2 * kMaxK * kMaxK);
   w.pts = reinterpret_cast<float*>(w.pcnt + 2 * kMaxK);
-  w.ldp = N | 1;  // odd row stride
+  w.ldp = pts_stride(N);
   w.sval = sval; w.sidx = sidx; w.changed = changed;
   return w;
 }
 
 // Seeding, Lloyd iterations, canonical relabelling and the outputs of segment s; the K leading coordinates of its n
-// points are already staged in w.pts (transposed).
+// points are already staged in w.pts (transposed).  KP = K rounded up to the register tile (4, 8, 16 or 32): a
+// thread holds its point in KP registers and reads the centres as float4 broadcasts, so the distance loops are
+// straight-line code.
+template <int KP>
 __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, int s, int row0, int n, int K) {
   float* cen = w.cen; float* mind = w.mind; int* lab = w.lab; int* map = w.map; float* part = w.part; int* pcnt = w.pcnt;
   float* pts = w.pts; float* sval = w.sval; int* sidx = w.sidx;
   const int ldp = w.ldp;
-  int& s_changed = *w.changed;
+  const int n4 = (n + 3) & ~3;
+  int flip = 0;
+  KPHASE_BEGIN();
   {
+    for (int e = threadIdx.x; e < K * LDC; e += kThreads) cen[e] = 0.f;
+    for (int i = threadIdx.x; i < n4; i += kThreads) lab[i] = -1;
+    __syncthreads();
     // ---- seeding
     if (P.init) {
       for (int e = threadIdx.x; e < K * K; e += kThreads)
         cen[(e / K) * LDC + (e % K)] = P.init[(static_cast<long long>(s) * P.Kmax + e / K) * P.Kmax + (e % K)];
-      __syncthreads();
     } else {
       int first = 0;
       if (P.weight) {
@@ -124,54 +190,67 @@ __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, i
           const float wt = P.weight[row0 + i];
           if (wt > bv) { bv = wt; bi = i; }
         }
-        first = block_argmax(bv, bi, sval, sidx);
+        first = block_argmax(bv, bi, sval, sidx, flip);
         if (first < 0 || first >= n) first = 0;
       }
-      for (int j = threadIdx.x; j < K; j += kThreads) cen[j] = pts[j * ldp + first];
-      __syncthreads();
-      for (int i = threadIdx.x; i < n; i += kThreads) mind[i] = sqdist(pts, ldp, i, cen, K);
-      for (int c = 1; c < K; ++c) {
+      // farthest-point seeding: the new centre is read straight from the point list by every thread; the running
+      // minimum distance of a thread's own points and the candidate for the next centre come out of the same loop
+      int nxt = first;
+      for (int c = 0; c < K; ++c) {
+        float cr[KP];
+        load_point<KP>(pts, ldp, nxt, K, cr);
+        for (int j = threadIdx.x; j < K; j += kThreads) cen[c * LDC + j] = pts[j * ldp + nxt];
         float bv = -INFINITY;
         int bi = 0x7fffffff;
-        for (int i = threadIdx.x; i < n; i += kThreads)
-          if (mind[i] > bv) { bv = mind[i]; bi = i; }
-        const int nxt = block_argmax(bv, bi, sval, sidx);
-        for (int j = threadIdx.x; j < K; j += kThreads) cen[c * LDC + j] = pts[j * ldp + nxt];
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kThreads) mind[i] = fminf(mind[i], sqdist(pts, ldp, i, cen + c * LDC, K));
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+          float p[KP];
+          load_point<KP>(pts, ldp, i, K, p);
+          const float d = sqdist<KP>(p, cr);
+          const float md = c == 0 ? d : fminf(mind[i], d);
+          mind[i] = md;
+          if (md > bv) { bv = md; bi = i; }
+        }
+        if (c + 1 < K) nxt = block_argmax(bv, bi, sval, sidx, flip);
       }
     }
-    for (int i = threadIdx.x; i < n; i += kThreads) lab[i] = -1;
     __syncthreads();
+    KPHASE_END(KP_SEED);
 
     // ---- Lloyd
     for (int it = 0; it < P.max_iter; ++it) {
-      if (threadIdx.x == 0) s_changed = 0;
-      __syncthreads();
       int changed = 0;
       for (int i = threadIdx.x; i < n; i += kThreads) {
+        float p[KP];
+        load_point<KP>(pts, ldp, i, K, p);
         float bd = INFINITY;
         int bc = 0;
+#pragma unroll 4
         for (int c = 0; c < K; ++c) {
-          const float d = sqdist(pts, ldp, i, cen + c * LDC, K);
+          const float d = sqdist<KP>(p, cen + c * LDC);
           if (d < bd) { bd = d; bc = c; }
         }
         if (lab[i] != bc) { lab[i] = bc; changed = 1; }
       }
-      if (changed) s_changed = 1;
-      __syncthreads();
-      if (!s_changed) break;
-      // partial sums over the two halves of the tokens (ascending order inside a half), then a fixed-order combine
-      const int nh = (n + 1) >> 1;
+      if (!__syncthreads_or(changed)) break;
+      // partial sums over the two halves of the tokens (ascending order inside a half, four tokens a step), then a
+      // fixed-order combine
+      const int nh = (((n + 1) >> 1) + 3) & ~3;
       for (int e = threadIdx.x; e < 2 * K * K; e += kThreads) {
         const int h = e / (K * K), r = e - h * K * K;
         const int c = r / K, d = r - c * K;
-        const int i0 = h * nh, i1 = min(n, i0 + nh);
-        const float* pd = pts + d * ldp;
+        const int i0 = h * nh, i1 = min(n4, i0 + nh);
+        const float4* pd = reinterpret_cast<const float4*>(pts + d * ldp + i0);
+        const int4* lp = reinterpret_cast<const int4*>(lab + i0);
         float sum = 0.f;
         int cnt = 0;
-        for (int i = i0; i < i1; ++i)
-          if (lab[i] == c) { sum += pd[i]; ++cnt; }
+        for (int q = 0; q < ((i1 - i0) >> 2); ++q) {
+          const float4 v = pd[q];
+          const int4 l = lp[q];
+          if (l.x == c) { sum += v.x; ++cnt; }
+          if (l.y == c) { sum += v.y; ++cnt; }
+          if (l.z == c) { sum += v.z; ++cnt; }
+          if (l.w == c) { sum += v.w; ++cnt; }
+        }
         part[h * kMaxK * kMaxK + r] = sum;
         if (d == 0) pcnt[h * kMaxK + c] = cnt;
       }
@@ -184,19 +263,31 @@ __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, i
       __syncthreads();
     }
 
-    // ---- canonical ids: clusters renamed in order of first occurrence
+    KPHASE_END(KP_LLOYD);
+    // ---- canonical ids: clusters renamed in order of first occurrence.  first[c] = lowest token of cluster c (an
+    //      integer minimum: order independent), new id = number of clusters that start earlier
+    int* first = pcnt;   // [K] (the partial counts are dead)
+    for (int c = threadIdx.x; c < K; c += kThreads) first[c] = 0x7fffffff;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kThreads) atomicMin(&first[lab[i]], i);
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += kThreads) {
+      const int f = first[c];
+      int rank = 0;
+      for (int c2 = 0; c2 < K; ++c2) rank += first[c2] < f ? 1 : 0;
+      map[c] = f == 0x7fffffff ? -1 : rank;
+    }
     if (threadIdx.x == 0) {
-      for (int c = 0; c < K; ++c) map[c] = -1;
-      int next = 0;
-      for (int i = 0; i < n && next < K; ++i)
-        if (map[lab[i]] < 0) map[lab[i]] = next++;
-      P.n_child[s] = next;
+      int used = 0;
+      for (int c = 0; c < K; ++c) used += first[c] != 0x7fffffff ? 1 : 0;
+      P.n_child[s] = used;
     }
     __syncthreads();
     if (P.labels)
       for (int i = threadIdx.x; i < n; i += kThreads) P.labels[row0 + i] = map[lab[i]];
     if (P.child)
       for (int i = threadIdx.x; i < n; i += kThreads) P.child[row0 + i] = map[lab[i]];
+    KPHASE_END(KP_RELABEL);
     if (P.centres) {
       float* co = P.centres + static_cast<long long>(s) * P.Kmax * P.Kmax;
       for (int e = threadIdx.x; e < P.Kmax * P.Kmax; e += kThreads) co[e] = 0.f;
@@ -240,6 +331,7 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
   const int ldp = w.ldp;
   constexpr int LD = kKwayMaxK + 1;
   int& s_changed = *w.changed;
+  int flip = 0;
   // unit rows
   for (int i = threadIdx.x; i < n; i += kThreads) {
     float ss = 0.f;
@@ -257,7 +349,7 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
       const float wt = P.weight[row0 + i];
       if (wt > bv) { bv = wt; bi = i; }
     }
-    first = block_argmax(bv, bi, w.sval, w.sidx);
+    first = block_argmax(bv, bi, w.sval, w.sidx, flip);
     if (first < 0 || first >= n) first = 0;
   }
   __syncthreads();
@@ -273,7 +365,7 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
       cacc[i] = c;
       if (-c > bv) { bv = -c; bi = i; }       // argmin c, ties -> lowest index
     }
-    const int nxt = block_argmax(bv, bi, w.sval, w.sidx);
+    const int nxt = block_argmax(bv, bi, w.sval, w.sidx, flip);
     for (int d = threadIdx.x; d < K; d += kThreads) R[d * LDC + j] = pts[d * ldp + nxt];
     __syncthreads();
   }
@@ -364,6 +456,13 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
   __syncthreads();
 }
 
+__device__ __forceinline__ void kmeans_dispatch(const Params& P, const Work& w, int s, int row0, int n, int K) {
+  if (K <= 4) kmeans_segment<4>(P, w, s, row0, n, K);
+  else if (K <= 8) kmeans_segment<8>(P, w, s, row0, n, K);
+  else if (K <= 16) kmeans_segment<16>(P, w, s, row0, n, K);
+  else kmeans_segment<32>(P, w, s, row0, n, K);
+}
+
 __device__ __forceinline__ int select_k(const Params& P, const float* __restrict__ lam, int n) {
   int K;
   if (P.n_clusters > 0) {
@@ -378,8 +477,8 @@ __device__ __forceinline__ int select_k(const Params& P, const float* __restrict
 
 __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ float sval[kThreads / 32];
-  __shared__ int sidx[kThreads / 32];
+  __shared__ float sval[2 * (kThreads / 32)];
+  __shared__ int sidx[2 * (kThreads / 32)];
   __shared__ int s_changed;
   __shared__ float kT[16 * 17], kS[16 * 17], kW[16 * 17];
   __shared__ __align__(16) float krot[32];
@@ -403,7 +502,7 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
     }
     __syncthreads();
     if (P.discretise == 1) kway_segment(P, w, ks, s, row0, n, K);
-    else kmeans_segment(P, w, s, row0, n, K);
+    else kmeans_dispatch(P, w, s, row0, n, K);
   }
 }
 
@@ -411,14 +510,15 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
 //   H_lead = W Theta W^T (Jacobi; the leading kconv columns if they converged as a block, else the whole block),
 //   V = D^1/2 U W, eigenvalues descending, canonical sign (largest-|entry| positive, ties -> lowest row), then the
 //   k-means of kmeans_kernel on the embedding that is already in shared memory.
-__global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, 7) ritz_kmeans_kernel(const Params P) {
   using G = ThreadGroup<0, kThreads, 0>;
   extern __shared__ __align__(16) float smem[];
-  __shared__ float sval[kThreads / 32];
-  __shared__ int sidx[kThreads / 32];
+  __shared__ float sval[2 * (kThreads / 32)];
+  __shared__ int sidx[2 * (kThreads / 32)];
   __shared__ int s_changed;
   constexpr int MB = 16, LD = MB + 1;
   __shared__ float Hm[MB * LD], Sm[MB * LD], Wm[MB * LD], theta[MB], sgn[MB], lam_s[MB];
+  __shared__ __align__(16) float Wt[MB * MB];   // Wt[c][a] = W[c][a], rows read as float4 broadcasts
   __shared__ __align__(16) float rot[4 * (MB / 2)];   // jacobi() stores the rotations as float4
   __shared__ int order[MB];
   const Work w = carve(smem, P.N, sval, sidx, &s_changed);
@@ -428,6 +528,19 @@ __global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
   for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
     const int row0 = s * n;
     __syncthreads();
+    KPHASE_BEGIN();
+    // this thread's (at most two) basis rows and degrees: requested now, they land while the Jacobi sweeps run
+    float4 ur[kRitzTokens][4];
+    float dg[kRitzTokens];
+#pragma unroll
+    for (int t = 0; t < kRitzTokens; ++t) {
+      const int i = threadIdx.x + t * kThreads;
+      if (i < n) {
+        const float4* up = reinterpret_cast<const float4*>(P.U + static_cast<size_t>(row0 + i) * MB);
+        ur[t][0] = __ldg(up); ur[t][1] = __ldg(up + 1); ur[t][2] = __ldg(up + 2); ur[t][3] = __ldg(up + 3);
+        dg[t] = __ldg(P.weight + row0 + i);
+      }
+    }
     for (int e = threadIdx.x; e < MB * MB; e += kThreads) Hm[(e >> 4) * LD + (e & 15)] = P.H[static_cast<size_t>(s) * 256 + e];
     __syncthreads();
     const int kk = P.kconv < m ? P.kconv : m;
@@ -437,6 +550,7 @@ __global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
       if (mdb <= m) md = mdb;
     }
     eig::jacobi<G>(Hm, Sm, LD, md, 12, rot);
+    KPHASE_END(KP_JACOBI);
     if (threadIdx.x < m) {
       const int a = threadIdx.x;
       const float ta = Hm[a * LD + a];
@@ -454,24 +568,29 @@ __global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < m * m; e += kThreads) {
-      const int c = e / m, a = e - c * m;
-      Wm[c * LD + a] = (c < md && a < md) ? Sm[a * LD + order[c]] : (a == c ? 1.f : 0.f);
+    for (int e = threadIdx.x; e < MB * MB; e += kThreads) {
+      const int c = e >> 4, a = e & 15;
+      Wt[e] = (c < m && a < m) ? ((c < md && a < md) ? Sm[a * LD + order[c]] : (a == c ? 1.f : 0.f)) : 0.f;
     }
     __syncthreads();
-    // v_c(i) = sqrt(d_i) sum_a W[c][a] u_a(i): one token per thread and step, the basis row straight from global memory
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-      const float4* up = reinterpret_cast<const float4*>(P.U + static_cast<size_t>(row0 + i) * MB);
-      const float4 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
-      const float u[16] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w, u2.x, u2.y, u2.z, u2.w, u3.x, u3.y, u3.z, u3.w};
-      const float sd = sqrtf(P.weight[row0 + i]);
-      for (int c = 0; c < k; ++c) {
-        float v = 0.f;
-        if (c < m) {
+    // v_c(i) = sqrt(d_i) sum_a W[c][a] u_a(i), written (transposed) to the embedding
 #pragma unroll
-          for (int a = 0; a < 16; ++a) v = fmaf(Wm[c * LD + a], u[a], v);
+    for (int t = 0; t < kRitzTokens; ++t) {
+      const int i = threadIdx.x + t * kThreads;
+      if (i < n) {
+        const float sd = sqrtf(dg[t]);
+        for (int c = 0; c < k; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int a4 = 0; a4 < 4; ++a4) {
+            const float4 wv = *reinterpret_cast<const float4*>(Wt + c * MB + 4 * a4);
+            acc = fmaf(wv.x, ur[t][a4].x, acc);
+            acc = fmaf(wv.y, ur[t][a4].y, acc);
+            acc = fmaf(wv.z, ur[t][a4].z, acc);
+            acc = fmaf(wv.w, ur[t][a4].w, acc);
+          }
+          w.pts[c * w.ldp + i] = acc * sd;
         }
-        w.pts[c * w.ldp + i] = v * sd;
       }
     }
     __syncthreads();
@@ -480,9 +599,9 @@ __global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
       float best = -1.f, bval = 0.f;
       int bidx = 0x7fffffff;
       for (int i = lane; i < n; i += 32) {
-        const float v = w.pts[c * w.ldp + i];
-        const float av = fabsf(v);
-        if (av > best) { best = av; bidx = i; bval = v; }
+        const float x = w.pts[c * w.ldp + i];
+        const float av = fabsf(x);
+        if (av > best) { best = av; bidx = i; bval = x; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -498,23 +617,43 @@ __global__ void __launch_bounds__(kThreads) ritz_kmeans_kernel(const Params P) {
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n * k; e += kThreads) {
-      const int i = e / k, c = e - i * k;
-      const float v = w.pts[c * w.ldp + i] * sgn[c];
-      P.Vout[static_cast<size_t>(row0) * k + e] = v;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < n * k; e += kThreads) {
-      const int c = e / n, i = e - c * n;
-      w.pts[c * w.ldp + i] *= sgn[c];
+    // signed eigenvectors: the thread's own rows go to global memory and back into the embedding
+    const bool vec4 = (k & 3) == 0 && (reinterpret_cast<uintptr_t>(P.Vout) & 15) == 0;
+#pragma unroll
+    for (int t = 0; t < kRitzTokens; ++t) {
+      const int i = threadIdx.x + t * kThreads;
+      if (i < n) {
+        float* vo = P.Vout + static_cast<size_t>(row0 + i) * k;
+        if (vec4) {
+          for (int c = 0; c < k; c += 4) {
+            float4 x;
+            x.x = w.pts[c * w.ldp + i] * sgn[c];
+            x.y = w.pts[(c + 1) * w.ldp + i] * sgn[c + 1];
+            x.z = w.pts[(c + 2) * w.ldp + i] * sgn[c + 2];
+            x.w = w.pts[(c + 3) * w.ldp + i] * sgn[c + 3];
+            w.pts[c * w.ldp + i] = x.x;
+            w.pts[(c + 1) * w.ldp + i] = x.y;
+            w.pts[(c + 2) * w.ldp + i] = x.z;
+            w.pts[(c + 3) * w.ldp + i] = x.w;
+            *reinterpret_cast<float4*>(vo + c) = x;
+          }
+        } else {
+          for (int c = 0; c < k; ++c) {
+            const float x = w.pts[c * w.ldp + i] * sgn[c];
+            w.pts[c * w.ldp + i] = x;
+            vo[c] = x;
+          }
+        }
+      }
     }
     __syncthreads();
     const int K = select_k(P, lam_s, n);
+    KPHASE_END(KP_ROTATE);
     if (P.discretise == 1) {
       const KwayScratch ks{Hm, Sm, Wm, rot};   // the Ritz step is done with them
       kway_segment(P, w, ks, s, row0, n, K);
     } else {
-      kmeans_segment(P, w, s, row0, n, K);
+      kmeans_dispatch(P, w, s, row0, n, K);
     }
   }
 }
@@ -556,8 +695,7 @@ extern "C" int msvit_discretise(const float* V, const float* lam, const float* w
   P.U = nullptr; P.H = nullptr; P.info = nullptr; P.Vout = nullptr; P.lam_out = nullptr; P.child = nullptr;
   P.m = 0; P.kconv = 0;
   const int kcap = P.Kmax < kMaxK ? P.Kmax : kMaxK;   // coordinates staged per point
-  const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N + 2 * kMaxK * kMaxK + static_cast<size_t>(kcap) * (N | 1)) +
-                      sizeof(int) * (N + kMaxK + 2 * kMaxK);
+  const size_t smem = work_bytes(N, kcap);
   if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_status(e);
@@ -576,6 +714,7 @@ extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* 
   if (!labels && !child) return MSVIT_ERR_NULL;
   if (S < 0 || N <= 0 || k <= 0 || total_rows < 0 || max_iter <= 0) return MSVIT_ERR_SHAPE;
   if (block != 16 || k > block || N <= block || n_converge < 0 || n_converge > block) return MSVIT_ERR_SHAPE;
+  if (N > kRitzTokens * kThreads) return MSVIT_ERR_SHAPE;   // the partner of ncut_fused_kernel (N <= 208)
   if (n_clusters > k) return MSVIT_ERR_SHAPE;
   if (method != MSVIT_DISC_KMEANS && method != MSVIT_DISC_AXIS_ALIGN) return MSVIT_ERR_MODE;
   if (total_rows != static_cast<int64_t>(S) * N) return MSVIT_ERR_SHAPE;
@@ -589,8 +728,7 @@ extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* 
   P.U = U; P.H = H; P.info = info; P.Vout = V; P.lam_out = lam; P.child = child;
   P.m = block; P.kconv = n_converge > 0 ? n_converge : k;
   P.discretise = method;
-  const size_t smem = sizeof(float) * (kMaxK * (kMaxK + 1) + N + 2 * kMaxK * kMaxK + static_cast<size_t>(k) * (N | 1)) +
-                      sizeof(int) * (N + kMaxK + 2 * kMaxK);
+  const size_t smem = work_bytes(N, k);
   if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(ritz_kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_status(e);
@@ -598,3 +736,16 @@ extern "C" int msvit_ritz_kmeans(const float* U, const float* H, const int32_t* 
   ritz_kmeans_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(P);
   return cuda_status(cudaGetLastError());
 }
+
+#ifdef KM_PROFILE
+extern "C" int msvit_km_profile(unsigned long long* host_out, int reset) {
+  using namespace msvit::km;
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, g_km_cycles, sizeof(unsigned long long) * KP_COUNT);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (reset) {
+    unsigned long long z[KP_COUNT] = {};
+    e = cudaMemcpyToSymbol(g_km_cycles, z, sizeof(z));
+  }
+  return static_cast<int>(e);
+}
+#endif

@@ -149,6 +149,139 @@ __global__ void __launch_bounds__(256) key_sums_kernel(const float* __restrict__
   }
 }
 
+
+// Both statistics from ONE pass over the attention tensor.  grid (cluster range z, image x head); the CTA groups the
+// image's queries by cluster (stable, group_tokens) and walks its clusters: a warp takes every 8th query row of the
+// cluster, reduces it over the keys of each cluster (transmitter row, as key_sums_kernel) and adds the same registers
+// into its running column sums; the eight warps' column sums are combined in warp order and divided by the cluster
+// size (receiver row).  Every attention element is loaded once: B*H*N*N*4 bytes read, (2 C / N) of that written.
+constexpr int kStatsChunks = 8;   // per-lane register chunks along the key axis: N <= 32 * 8 * VEC
+
+template <int CMAX, int VEC>
+__device__ __forceinline__ void stats_row(const float* __restrict__ row, const int* lab, int N, int lane,
+                                          float (&acc)[CMAX], float (&col)[kStatsChunks][VEC]) {
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kStatsChunks; ++j) {
+    const int k = (j * 32 + lane) * VEC;
+    if (k < N) {
+      if constexpr (VEC == 4) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(row + k));
+        const int4 l = *reinterpret_cast<const int4*>(lab + k);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          acc[c] += (l.x == c ? a.x : 0.f) + (l.y == c ? a.y : 0.f) + (l.z == c ? a.z : 0.f) + (l.w == c ? a.w : 0.f);
+        col[j][0] += a.x; col[j][1] += a.y; col[j][2] += a.z; col[j][3] += a.w;
+      } else {
+        const float a = __ldcs(row + k);
+        const int l = lab[k];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) acc[c] += l == c ? a : 0.f;
+        col[j][0] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  }
+}
+
+template <int CMAX, int VEC>
+__global__ void __launch_bounds__(256) attention_stats_kernel(const float* __restrict__ attn,
+                                                              const int64_t* __restrict__ cluster_indices,
+                                                              float* __restrict__ tr, float* __restrict__ rc, int H,
+                                                              int N, int C) {
+  extern __shared__ int sm[];
+  const int N4 = (N + 3) & ~3;
+  int* lab = sm;                    // [N4]   label or -1 (pad = -1)
+  int* order = lab + N4;            // [N]    queries grouped by cluster
+  int* start = order + N;           // [C+1]
+  int* cursor = start + C + 1;      // [C]
+  float* part = reinterpret_cast<float*>(cursor + C);   // [8][N4]
+  const int bh = blockIdx.y, b = bh / H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (threadIdx.x < N4 - N) lab[N + threadIdx.x] = -1;
+  group_tokens(cluster_indices + static_cast<size_t>(b) * N, lab, order, start, cursor, N, C);
+
+  const int c0 = static_cast<int>(static_cast<long long>(blockIdx.x) * C / gridDim.x);
+  const int c1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * C / gridDim.x);
+  const float* base = attn + static_cast<size_t>(bh) * N * N;
+  float acc[CMAX];
+  float col[kStatsChunks][VEC];
+  for (int c = c0; c < c1; ++c) {
+    const int s0 = start[c], s1 = start[c + 1];
+#pragma unroll
+    for (int j = 0; j < kStatsChunks; ++j)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) col[j][v] = 0.f;
+    for (int i = s0 + warp; i < s1; i += nwarps) {
+      const int q = order[i];
+      stats_row<CMAX, VEC>(base + static_cast<size_t>(q) * N, lab, N, lane, acc, col);
+      float* o = tr + (static_cast<size_t>(bh) * N + q) * C;
+#pragma unroll
+      for (int cc = 0; cc < CMAX; ++cc)
+        if (lane == (cc & 31) && cc < C) o[cc] = acc[cc];
+    }
+#pragma unroll
+    for (int j = 0; j < kStatsChunks; ++j) {
+      const int k = (j * 32 + lane) * VEC;
+      if (k < N) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) part[warp * N4 + k + v] = col[j][v];
+      }
+    }
+    __syncthreads();
+    const float inv = s1 > s0 ? 1.0f / static_cast<float>(s1 - s0) : 0.f;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += part[w * N4 + k];
+      rc[(static_cast<size_t>(bh) * C + c) * N + k] = s * inv;
+    }
+    __syncthreads();
+  }
+  // queries whose label is outside [0, C) belong to no receiver row but still have a transmitter row
+  if (blockIdx.x == 0) {
+    for (int q = warp; q < N; q += nwarps) {
+      if (lab[q] >= 0) continue;
+      stats_row<CMAX, VEC>(base + static_cast<size_t>(q) * N, lab, N, lane, acc, col);
+      float* o = tr + (static_cast<size_t>(bh) * N + q) * C;
+#pragma unroll
+      for (int cc = 0; cc < CMAX; ++cc)
+        if (lane == (cc & 31) && cc < C) o[cc] = acc[cc];
+    }
+  }
+}
+
+template <int CMAX, int VEC>
+static int launch_stats(const float* attn, const int64_t* ci, float* tr, float* rc, int B, int H, int N, int C,
+                        cudaStream_t stream) {
+  const int N4 = (N + 3) & ~3;
+  const size_t ints = static_cast<size_t>(N4) + N + 2 * C + 1;
+  const size_t smem = sizeof(int) * ints + sizeof(float) * 8 * static_cast<size_t>(N4);
+  long long z = (4LL * sm_count() + static_cast<long long>(B) * H - 1) / (static_cast<long long>(B) * H);
+  if (z > 8) z = 8;
+  if (z > C) z = C;
+  if (z < 1) z = 1;
+  cudaError_t e = cudaFuncSetAttribute(attention_stats_kernel<CMAX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_status(e);
+  attention_stats_kernel<CMAX, VEC><<<dim3(static_cast<unsigned>(z), B * H), 256, smem, stream>>>(attn, ci, tr, rc, H,
+                                                                                                N, C);
+  return cuda_status(cudaGetLastError());
+}
+
+template <int VEC>
+static int dispatch_stats(const float* attn, const int64_t* ci, float* tr, float* rc, int B, int H, int N, int C,
+                          cudaStream_t stream) {
+  if (C <= 8) return launch_stats<8, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
+  if (C <= 16) return launch_stats<16, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
+  if (C <= 32) return launch_stats<32, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
+  return launch_stats<64, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
+}
+
 }  // namespace mask
 }  // namespace msvit
 
@@ -168,4 +301,21 @@ extern "C" int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_
   else if (C <= 32) mask::key_sums_kernel<32><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
   else mask::key_sums_kernel<64><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
   return cuda_status(cudaGetLastError());
+}
+
+// transmitter [B, H, N, C] and receiver [B, H, C, N] statistics in one pass over attn [B, H, N, N]
+// (modeling_msvitencoder.py:182-190).  MSVIT_ERR_SHAPE for N beyond the register-resident row (N > 1024, or N > 256
+// when N is not a multiple of 4): those shapes take msvit_cluster_key_sums + msvit_pool.
+extern "C" int msvit_cluster_attention_stats(const float* attn, const int64_t* cluster_indices, float* transmitter,
+                                             float* receiver, int B, int H, int N, int C, msvit_stream_t stream_) {
+  using namespace msvit;
+  if (!attn || !cluster_indices || !transmitter || !receiver) return MSVIT_ERR_NULL;
+  if (B < 0 || H <= 0 || N <= 0 || C <= 0 || C > 64 || static_cast<long long>(B) * H > 65535) return MSVIT_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(attn) & 15) != 0) return MSVIT_ERR_ALIGN;
+  const bool vec = (N & 3) == 0;
+  if (N > 32 * mask::kStatsChunks * (vec ? 4 : 1)) return MSVIT_ERR_SHAPE;
+  if (B == 0) return MSVIT_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return vec ? mask::dispatch_stats<4>(attn, cluster_indices, transmitter, receiver, B, H, N, C, stream)
+             : mask::dispatch_stats<1>(attn, cluster_indices, transmitter, receiver, B, H, N, C, stream);
 }

@@ -745,7 +745,8 @@ extern "C" int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U
 
   const size_t fixed = 1024 + kUopBytes + ((sizeof(Shared) + 15) & ~size_t(15)) +
                        static_cast<size_t>(make_eig_layout().total) * sizeof(float);
-  const size_t kMaxSmem = 227 * 1024;
+  size_t kMaxSmem = 227 * 1024;
+  if (const char* rs = getenv("MSVIT_FUSED_RESERVE_KB")) kMaxSmem -= static_cast<size_t>(atoi(rs)) * 1024;   // development
   int stages = static_cast<int>((kMaxSmem - fixed) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return MSVIT_ERR_SHAPE;

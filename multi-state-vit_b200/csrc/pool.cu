@@ -46,6 +46,8 @@ struct Loader<__nv_bfloat16, 1> {
   }
 };
 
+// grid (image, column slab, cluster range): CTA z owns clusters [z K / Z, (z+1) K / Z) so that a small batch of long
+// images still fills the machine; every CTA of an image repeats the (cheap) grouping.
 template <typename T, int VEC>
 __global__ void pool_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, float* __restrict__ pooled,
                             int32_t* __restrict__ counts, int N, int D, int K) {
@@ -53,64 +55,31 @@ __global__ void pool_kernel(const T* __restrict__ x, const int64_t* __restrict__
   int* lab = sm;            // [N]   label or -1
   int* order = lab + N;     // [N]   tokens grouped by label, ascending token id inside a group
   int* start = order + N;   // [K+1] group offsets
+  int* cursor = start + K + 1;  // [K]
   const int b = blockIdx.x;
-  const int64_t* lb = labels + static_cast<long long>(b) * N;
-
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const long long l = lb[i];
-    lab[i] = (l >= 0 && l < K) ? static_cast<int>(l) : -1;
-  }
-  for (int c = threadIdx.x; c <= K; c += blockDim.x) start[c] = 0;
-  __syncthreads();
-  // histogram (integer shared-memory atomics: order independent, hence deterministic)
-  for (int i = threadIdx.x; i < N; i += blockDim.x)
-    if (lab[i] >= 0) atomicAdd(&start[lab[i] + 1], 1);
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    // inclusive scan of start[1..K] by one warp
-    int carry = 0;
-    for (int base = 1; base <= K; base += 32) {
-      const int idx = base + threadIdx.x;
-      int v = idx <= K ? start[idx] : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (static_cast<int>(threadIdx.x) >= o) v += u;
-      }
-      if (idx <= K) start[idx] = v + carry;
-      carry += __shfl_sync(0xffffffffu, v, 31);
-    }
-  }
-  __syncthreads();
-  // stable placement: rank among earlier tokens with the same label
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const int l = lab[i];
-    if (l < 0) continue;
-    int r = 0;
-    for (int j = 0; j < i; ++j) r += lab[j] == l ? 1 : 0;
-    order[start[l] + r] = i;
-  }
-  __syncthreads();
-  if (blockIdx.y == 0)
+  group_tokens(labels + static_cast<long long>(b) * N, lab, order, start, cursor, N, K);
+  if (blockIdx.y == 0 && blockIdx.z == 0)
     for (int c = threadIdx.x; c < K; c += blockDim.x)
       counts[static_cast<long long>(b) * K + c] = start[c + 1] - start[c];
 
   const int col = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
   if (col >= D) return;
+  const int c0 = static_cast<int>(static_cast<long long>(blockIdx.z) * K / gridDim.z);
+  const int c1 = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * K / gridDim.z);
   const T* xb = x + static_cast<long long>(b) * N * D + col;
   float* pb = pooled + static_cast<long long>(b) * K * D + col;
-  for (int c = 0; c < K; ++c) {
+  for (int c = c0; c < c1; ++c) {
     const int s0 = start[c], s1 = start[c + 1];
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     int i = s0;
-    for (; i + 4 <= s1; i += 4) {
-      const int t0 = order[i], t1 = order[i + 1], t2 = order[i + 2], t3 = order[i + 3];
-      Loader<T, VEC>::add(xb + static_cast<long long>(t0) * D, acc);
-      Loader<T, VEC>::add(xb + static_cast<long long>(t1) * D, acc);
-      Loader<T, VEC>::add(xb + static_cast<long long>(t2) * D, acc);
-      Loader<T, VEC>::add(xb + static_cast<long long>(t3) * D, acc);
+    for (; i + 8 <= s1; i += 8) {
+      int t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = order[i + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) Loader<T, VEC>::add(xb + static_cast<long long>(t[u]) * D, acc);
     }
     for (; i < s1; ++i) Loader<T, VEC>::add(xb + static_cast<long long>(order[i]) * D, acc);
     const float inv = s1 > s0 ? 1.0f / static_cast<float>(s1 - s0) : 0.f;
@@ -132,13 +101,19 @@ static int launch(const void* x, const int64_t* labels, float* pooled, int32_t* 
   int threads = round_up(cols, 32);
   if (threads > 256) threads = 256;
   const int ysplit = ceil_div(cols, threads);
-  const size_t smem = sizeof(int) * (2 * static_cast<size_t>(N) + K + 1);
+  const size_t smem = sizeof(int) * (2 * static_cast<size_t>(N) + 2 * static_cast<size_t>(K) + 1);
   if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;
+  // enough CTAs for 8 per SM; the cluster split stops at 8 ranges (each CTA repeats the grouping)
+  const long long ctas = static_cast<long long>(B) * ysplit;
+  long long zsplit = (8LL * sm_count() + ctas - 1) / ctas;
+  if (zsplit > 8) zsplit = 8;
+  if (zsplit > K) zsplit = K;
+  if (zsplit < 1) zsplit = 1;
   cudaError_t e = cudaFuncSetAttribute(pool_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_status(e);
-  pool_kernel<T, VEC><<<dim3(B, ysplit), threads, smem, stream>>>(static_cast<const T*>(x), labels, pooled, counts, N,
-                                                                 D, K);
+  pool_kernel<T, VEC><<<dim3(B, ysplit, static_cast<unsigned>(zsplit)), threads, smem, stream>>>(
+      static_cast<const T*>(x), labels, pooled, counts, N, D, K);
   return cuda_status(cudaGetLastError());
 }
 

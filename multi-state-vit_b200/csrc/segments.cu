@@ -50,11 +50,23 @@ __global__ void __launch_bounds__(kThreads) build_segments_kernel(const int64_t*
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < N; i += kThreads) {
-    const int p = par[i];
-    int r = 0;
-    for (int j = 0; j < i; ++j) r += par[j] == p ? 1 : 0;
-    perm[b * N + start[p] + r] = b * N + i;
+  // stable placement by one warp, 32 tokens a step: `match.any` ranks a lane among the lanes with the same parent,
+  // start[p] doubles as the running cursor of parent p
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const unsigned below = (1u << lane) - 1u;
+    for (int base = 0; base < N; base += 32) {
+      const int i = base + lane;
+      const int p = i < N ? par[i] : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, p);
+      const int at = p >= 0 ? start[p] : 0;
+      __syncwarp();
+      if (p >= 0) {
+        perm[b * N + at + __popc(peers & below)] = b * N + i;
+        if ((peers & below) == 0) start[p] = at + __popc(peers);
+      }
+      __syncwarp();
+    }
   }
 }
 

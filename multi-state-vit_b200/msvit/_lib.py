@@ -53,6 +53,7 @@ _SIGNATURES = {
     "msvit_gkm_finalize": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr]),
     "msvit_attention_mask": (_c_int, [_c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr]),
     "msvit_cluster_key_sums": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr]),
+    "msvit_cluster_attention_stats": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr]),
 }
 
 

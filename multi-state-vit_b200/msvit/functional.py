@@ -112,6 +112,8 @@ class ClusterPlan:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("msvit.cluster_tokens runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if dev.index is None:   # "cuda" means the current device; tensors report an explicit index
+            dev = torch.device("cuda", torch.cuda.current_device())
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"tokens must be float32 or bfloat16, got {dtype}")
         self.lib = _lib.load()
@@ -157,6 +159,8 @@ class ClusterPlan:
                 self.seg_off = torch.empty(self.S + 1, **i32)
                 self.a_off = torch.empty(self.S + 1, dtype=torch.int64, device=dev)
                 self.xs = torch.empty(rows, D, dtype=dtype, device=dev)
+                self.V_tok = torch.empty(rows, k, **f32)
+                self.deg_tok = torch.empty(rows, **f32)
                 a_numel = B * ops.affinity_stride(N)
             self.A = torch.empty(a_numel, **f32)
             self.deg = torch.empty(rows, **f32)
@@ -248,11 +252,11 @@ class ClusterPlan:
             mark(6)
 
         if self.perm is not None:
+            # eigenvectors / degree back in token order (plan-owned buffers: no allocation per run)
             idx = self.perm.long()
-            V_tok = torch.empty_like(self.V)
-            V_tok[idx] = self.V
-            deg_tok = torch.empty_like(self.deg)
-            deg_tok[idx] = self.deg
+            self.V_tok.index_copy_(0, idx, self.V)
+            self.deg_tok.index_copy_(0, idx, self.deg)
+            V_tok, deg_tok = self.V_tok, self.deg_tok
         else:
             V_tok, deg_tok = self.V, self.deg
         aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0 and not self.fused) else None
@@ -393,6 +397,13 @@ def cluster_attention_stats(attention_probs: torch.Tensor, cluster_indices: torc
     with torch.cuda.device(a.device):
         tr = torch.empty(B, H, N, C, dtype=torch.float32, device=a.device)
         st = torch.cuda.current_stream(a.device).cuda_stream
+        if N <= (1024 if N % 4 == 0 else 256):
+            # one pass over the attention tensor for both statistics
+            rc = torch.empty(B, H, C, N, dtype=torch.float32, device=a.device)
+            _lib.check(_lib.load().msvit_cluster_attention_stats(ops._ptr(a), ops._ptr(lab), ops._ptr(tr), ops._ptr(rc),
+                                                                 B, H, N, C, st), "msvit_cluster_attention_stats")
+            return tr, rc
+        # longer rows: key sums, then the query means as cluster-mean pooling of the [B*H, N, N] view (two passes)
         _lib.check(_lib.load().msvit_cluster_key_sums(ops._ptr(a), ops._ptr(lab), ops._ptr(tr), B, H, N, C, st),
                    "msvit_cluster_key_sums")
         lab_h = lab[:, None, :].expand(B, H, N).reshape(B * H, N).contiguous()
@@ -421,6 +432,8 @@ class HostClusterer:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("msvit.HostClusterer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.B, self.N, self.D, self.dtype, self.device = int(B), int(N), int(D), dtype, dev
         self.chunk = max(1, min(int(chunk), self.B))
         self.bounds = [(b0, min(self.B, b0 + self.chunk)) for b0 in range(0, self.B, self.chunk)]

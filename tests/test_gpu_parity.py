@@ -328,7 +328,8 @@ def test_ncut_eig_partial_convergence_request():
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 196, 8), (1, 2, 50, 5), (2, 1, 33, 12), (1, 4, 256, 20), (1, 2, 784, 39),
-                                   (1, 1, 300, 64)])
+                                   (1, 1, 300, 64), (1, 2, 197, 8), (1, 1, 1024, 16), (64, 12, 196, 8),
+                                   (1, 1, 1100, 8), (1, 1, 301, 5)])   # the last two take the two-pass route
 def test_cluster_attention_stats_match_reference_restatement(shape):
     # compress_tokens_with_cluster_indices (msvitencoder.py:182-190): transmitter sums and receiver means
     B, H, N, C = shape
@@ -341,6 +342,18 @@ def test_cluster_attention_stats_match_reference_restatement(shape):
     torch.testing.assert_close(tr.cpu().double(), tr_ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(rc.cpu().double(), rc_ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(tr.sum(-1).cpu(), torch.ones(B, H, N), rtol=1e-5, atol=1e-5)   # rows of a softmax
+
+
+def test_cluster_attention_stats_labels_outside_the_cluster_range():
+    # a query whose label is >= n_clusters joins no receiver row but keeps its transmitter row
+    B, H, N, C = 2, 2, 64, 4
+    g = torch.Generator().manual_seed(5)
+    attn = torch.softmax(torch.randn(B, H, N, N, generator=g), dim=-1)
+    lab = torch.randint(0, C + 2, (B, N), generator=g)
+    tr_ref, rc_ref = O.cluster_attention_stats(attn.double(), lab, C)
+    tr, rc = msvit.cluster_attention_stats(attn.to(DEV), lab.to(DEV), C)
+    torch.testing.assert_close(tr.cpu().double(), tr_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rc.cpu().double(), rc_ref, rtol=1e-5, atol=1e-6)
 
 
 def test_cluster_tokens_cosine_distance_matches_oracle():
