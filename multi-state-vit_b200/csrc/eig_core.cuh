@@ -1004,27 +1004,25 @@ __device__ __forceinline__ void jacobi_warp8(float* H, float* Sm, int ld, int md
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     bool big = false;
     for (int r = 0; r < md - 1; ++r) {
-      int p1 = 0, q1 = 1, p2 = 0, q2 = 1;
-      float c1 = 1.f, s1 = 0.f, c2 = 1.f, s2 = 0.f;
-      float npp = 0.f, npq = 0.f, nqp = 0.f, nqq = 0.f, nsp = 0.f, nsq = 0.f;
-      if (lane < ns) {
-        pair_of(tb, r, p2, q2);
-        jacobi_rot(H[p2 * ld + p2], H[q2 * ld + q2], H[p2 * ld + q2], c2, s2, big);
-        const float sp = Sm[ta * ld + p2], sq = Sm[ta * ld + q2];
-        nsp = c2 * sp - s2 * sq;
-        nsq = s2 * sp + c2 * sq;
-      }
-      if (lane < nb) {
-        pair_of(ta, r, p1, q1);
-        bool unused = false;
-        jacobi_rot(H[p1 * ld + p1], H[q1 * ld + q1], H[p1 * ld + q1], c1, s1, unused);
-        const float hpp = H[p1 * ld + p2], hpq = H[p1 * ld + q2], hqp = H[q1 * ld + p2], hqq = H[q1 * ld + q2];
-        const float rpp = c1 * hpp - s1 * hqp, rpq = c1 * hpq - s1 * hqq;
-        const float rqp = s1 * hpp + c1 * hqp, rqq = s1 * hpq + c1 * hqq;
-        npp = c2 * rpp - s2 * rpq; npq = s2 * rpp + c2 * rpq;
-        nqp = c2 * rqp - s2 * rqq; nqq = s2 * rqp + c2 * rqq;
-        if (ta == tb) { npq = 0.f; nqp = 0.f; }
-      }
+      // every lane runs both rotations and both updates on valid addresses (lanes past the item counts repeat an
+      // earlier item and drop the result): no divergence, the two dependent chains overlap
+      const int tr = ta % half;                       // row pair of the 2 x 2 block
+      const int sa = lane < ns ? ta : 0;              // row of the S slice
+      int p1, q1, p2, q2;
+      pair_of(tb, r, p2, q2);
+      pair_of(tr, r, p1, q1);
+      float c1, s1, c2, s2;
+      bool unused = false;
+      jacobi_rot(H[p2 * ld + p2], H[q2 * ld + q2], H[p2 * ld + q2], c2, s2, big);
+      jacobi_rot(H[p1 * ld + p1], H[q1 * ld + q1], H[p1 * ld + q1], c1, s1, unused);
+      const float sp = Sm[sa * ld + p2], sq = Sm[sa * ld + q2];
+      const float nsp = c2 * sp - s2 * sq, nsq = s2 * sp + c2 * sq;
+      const float hpp = H[p1 * ld + p2], hpq = H[p1 * ld + q2], hqp = H[q1 * ld + p2], hqq = H[q1 * ld + q2];
+      const float rpp = c1 * hpp - s1 * hqp, rpq = c1 * hpq - s1 * hqq;
+      const float rqp = s1 * hpp + c1 * hqp, rqq = s1 * hpq + c1 * hqq;
+      float npp = c2 * rpp - s2 * rpq, npq = s2 * rpp + c2 * rpq;
+      float nqp = c2 * rqp - s2 * rqq, nqq = s2 * rqp + c2 * rqq;
+      if (tr == tb) { npq = 0.f; nqp = 0.f; }
       __syncwarp();
       if (lane < ns) { Sm[ta * ld + p2] = nsp; Sm[ta * ld + q2] = nsq; }
       if (lane < nb) {

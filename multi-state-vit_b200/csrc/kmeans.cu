@@ -10,6 +10,8 @@
 // so a warp reads it without bank conflicts).  Distance + argmin run in one pass per point; the centre update is a
 // segmented, atomic-free sum in a fixed order (thread (c, d, h) adds the members of cluster c in ascending token
 // order over half h of the tokens, the halves are combined in a fixed order).
+#include <cstdlib>
+
 #include "eig_core.cuh"
 
 namespace msvit {
@@ -60,9 +62,10 @@ struct Params {
 // block-wide argmax of (value, index) with ties -> lowest index; result returned to all threads.  One barrier per
 // call: every thread combines the per-warp winners itself, and consecutive calls alternate between the two halves
 // of sval / sidx (`flip`), so a call never overwrites what a slower thread is still reading.
+template <class G>
 __device__ __forceinline__ int block_argmax(float v, int idx, float* sval, int* sidx, int& flip) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int W = kThreads / 32;
+  const int lane = G::tid() & 31, warp = G::tid() >> 5;
+  constexpr int W = G::kThreads / 32;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, v, o);
@@ -73,7 +76,7 @@ __device__ __forceinline__ int block_argmax(float v, int idx, float* sval, int* 
   int* si = sidx + flip * W;
   flip ^= 1;
   if (lane == 0) { sv[warp] = v; si[warp] = idx; }
-  __syncthreads();
+  G::sync();
   v = sv[0]; idx = si[0];
 #pragma unroll
   for (int w = 1; w < W; ++w) {
@@ -82,6 +85,27 @@ __device__ __forceinline__ int block_argmax(float v, int idx, float* sval, int* 
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
   return idx;
+}
+
+// The same for values >= +0 (squared distances), where the bit pattern orders like the value: two warp reductions
+// (redux.sync) per level instead of a shuffle tree.  A thread without a candidate passes (0, 0x7fffffff).
+template <class G>
+__device__ __forceinline__ int block_argmax_nonneg(float v, int idx, float* sval, int* sidx, int& flip) {
+  const int lane = G::tid() & 31, warp = G::tid() >> 5;
+  constexpr int W = G::kThreads / 32;
+  static_assert(W <= 32, "one lane per warp in the second level");
+  const unsigned key = __float_as_uint(v);
+  const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+  const int widx = __reduce_min_sync(0xffffffffu, key == wmax ? idx : 0x7fffffff);
+  unsigned* sk = reinterpret_cast<unsigned*>(sval) + flip * W;
+  int* si = sidx + flip * W;
+  flip ^= 1;
+  if (lane == 0) { sk[warp] = wmax; si[warp] = widx; }
+  G::sync();
+  const unsigned k2 = lane < W ? sk[lane] : 0u;
+  const int i2 = lane < W ? si[lane] : 0x7fffffff;
+  const unsigned bmax = __reduce_max_sync(0xffffffffu, k2);
+  return __reduce_min_sync(0xffffffffu, k2 == bmax ? i2 : 0x7fffffff);
 }
 
 // Point i of the transposed embedding (row stride ldp) in registers, coordinates beyond K read as 0.
@@ -165,32 +189,56 @@ __device__ __forceinline__ Work carve(float* smem, int N, float* sval, int* sidx
 // points are already staged in w.pts (transposed).  KP = K rounded up to the register tile (4, 8, 16 or 32): a
 // thread holds its point in KP registers and reads the centres as float4 broadcasts, so the distance loops are
 // straight-line code.
-template <int KP>
+template <int KP, class G>
 __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, int s, int row0, int n, int K) {
+  constexpr int kT = G::kThreads;
+  const int tid = G::tid();
   float* cen = w.cen; float* mind = w.mind; int* lab = w.lab; int* map = w.map; float* part = w.part; int* pcnt = w.pcnt;
   float* pts = w.pts; float* sval = w.sval; int* sidx = w.sidx;
   const int ldp = w.ldp;
   const int n4 = (n + 3) & ~3;
   int flip = 0;
+  // a thread's first two points stay in registers for the whole segment (KP <= 8); further points (segments of
+  // more than 2 * kT tokens) are re-read from shared memory
+  constexpr bool kCache = KP <= 8;
+  float pc[kCache ? 2 : 1][KP];
+  const int i0 = tid, i1 = tid + kT;
+  if constexpr (kCache) {
+    if (i0 < n) load_point<KP>(pts, ldp, i0, K, pc[0]);
+    if (i1 < n) load_point<KP>(pts, ldp, i1, K, pc[1]);
+  }
+  auto each_point = [&](auto&& f) {
+    int i = i0;
+    if constexpr (kCache) {
+      if (i0 < n) f(i0, pc[0]);
+      if (i1 < n) f(i1, pc[1]);
+      i = i1 + kT;
+    }
+    for (; i < n; i += kT) {
+      float p[KP];
+      load_point<KP>(pts, ldp, i, K, p);
+      f(i, p);
+    }
+  };
   KPHASE_BEGIN();
   {
-    for (int e = threadIdx.x; e < K * LDC; e += kThreads) cen[e] = 0.f;
-    for (int i = threadIdx.x; i < n4; i += kThreads) lab[i] = -1;
-    __syncthreads();
+    for (int e = tid; e < K * LDC; e += kT) cen[e] = 0.f;
+    for (int i = tid; i < n4; i += kT) lab[i] = -1;
+    G::sync();
     // ---- seeding
     if (P.init) {
-      for (int e = threadIdx.x; e < K * K; e += kThreads)
+      for (int e = tid; e < K * K; e += kT)
         cen[(e / K) * LDC + (e % K)] = P.init[(static_cast<long long>(s) * P.Kmax + e / K) * P.Kmax + (e % K)];
     } else {
       int first = 0;
       if (P.weight) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
+        for (int i = tid; i < n; i += kT) {
           const float wt = P.weight[row0 + i];
           if (wt > bv) { bv = wt; bi = i; }
         }
-        first = block_argmax(bv, bi, sval, sidx, flip);
+        first = block_argmax<G>(bv, bi, sval, sidx, flip);
         if (first < 0 || first >= n) first = 0;
       }
       // farthest-point seeding: the new centre is read straight from the point list by every thread; the running
@@ -199,29 +247,25 @@ __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, i
       for (int c = 0; c < K; ++c) {
         float cr[KP];
         load_point<KP>(pts, ldp, nxt, K, cr);
-        for (int j = threadIdx.x; j < K; j += kThreads) cen[c * LDC + j] = pts[j * ldp + nxt];
-        float bv = -INFINITY;
+        for (int j = tid; j < K; j += kT) cen[c * LDC + j] = pts[j * ldp + nxt];
+        float bv = 0.f;
         int bi = 0x7fffffff;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
-          float p[KP];
-          load_point<KP>(pts, ldp, i, K, p);
+        each_point([&](int i, const float (&p)[KP]) {
           const float d = sqdist<KP>(p, cr);
           const float md = c == 0 ? d : fminf(mind[i], d);
           mind[i] = md;
-          if (md > bv) { bv = md; bi = i; }
-        }
-        if (c + 1 < K) nxt = block_argmax(bv, bi, sval, sidx, flip);
+          if (bi == 0x7fffffff || md > bv) { bv = md; bi = i; }
+        });
+        if (c + 1 < K) nxt = block_argmax_nonneg<G>(bv, bi, sval, sidx, flip);
       }
     }
-    __syncthreads();
+    G::sync();
     KPHASE_END(KP_SEED);
 
     // ---- Lloyd
     for (int it = 0; it < P.max_iter; ++it) {
       int changed = 0;
-      for (int i = threadIdx.x; i < n; i += kThreads) {
-        float p[KP];
-        load_point<KP>(pts, ldp, i, K, p);
+      each_point([&](int i, const float (&p)[KP]) {
         float bd = INFINITY;
         int bc = 0;
 #pragma unroll 4
@@ -230,12 +274,12 @@ __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, i
           if (d < bd) { bd = d; bc = c; }
         }
         if (lab[i] != bc) { lab[i] = bc; changed = 1; }
-      }
-      if (!__syncthreads_or(changed)) break;
+      });
+      if (!G::sync_or(changed != 0)) break;
       // partial sums over the two halves of the tokens (ascending order inside a half, four tokens a step), then a
       // fixed-order combine
       const int nh = (((n + 1) >> 1) + 3) & ~3;
-      for (int e = threadIdx.x; e < 2 * K * K; e += kThreads) {
+      for (int e = tid; e < 2 * K * K; e += kT) {
         const int h = e / (K * K), r = e - h * K * K;
         const int c = r / K, d = r - c * K;
         const int i0 = h * nh, i1 = min(n4, i0 + nh);
@@ -254,50 +298,50 @@ __device__ __forceinline__ void kmeans_segment(const Params& P, const Work& w, i
         part[h * kMaxK * kMaxK + r] = sum;
         if (d == 0) pcnt[h * kMaxK + c] = cnt;
       }
-      __syncthreads();
-      for (int r = threadIdx.x; r < K * K; r += kThreads) {
+      G::sync();
+      for (int r = tid; r < K * K; r += kT) {
         const int c = r / K, d = r - c * K;
         const int cnt = pcnt[c] + pcnt[kMaxK + c];
         if (cnt > 0) cen[c * LDC + d] = (part[r] + part[kMaxK * kMaxK + r]) / static_cast<float>(cnt);
       }
-      __syncthreads();
+      G::sync();
     }
 
     KPHASE_END(KP_LLOYD);
     // ---- canonical ids: clusters renamed in order of first occurrence.  first[c] = lowest token of cluster c (an
     //      integer minimum: order independent), new id = number of clusters that start earlier
     int* first = pcnt;   // [K] (the partial counts are dead)
-    for (int c = threadIdx.x; c < K; c += kThreads) first[c] = 0x7fffffff;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kThreads) atomicMin(&first[lab[i]], i);
-    __syncthreads();
-    for (int c = threadIdx.x; c < K; c += kThreads) {
+    for (int c = tid; c < K; c += kT) first[c] = 0x7fffffff;
+    G::sync();
+    for (int i = tid; i < n; i += kT) atomicMin(&first[lab[i]], i);
+    G::sync();
+    for (int c = tid; c < K; c += kT) {
       const int f = first[c];
       int rank = 0;
       for (int c2 = 0; c2 < K; ++c2) rank += first[c2] < f ? 1 : 0;
       map[c] = f == 0x7fffffff ? -1 : rank;
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       int used = 0;
       for (int c = 0; c < K; ++c) used += first[c] != 0x7fffffff ? 1 : 0;
       P.n_child[s] = used;
     }
-    __syncthreads();
+    G::sync();
     if (P.labels)
-      for (int i = threadIdx.x; i < n; i += kThreads) P.labels[row0 + i] = map[lab[i]];
+      for (int i = tid; i < n; i += kT) P.labels[row0 + i] = map[lab[i]];
     if (P.child)
-      for (int i = threadIdx.x; i < n; i += kThreads) P.child[row0 + i] = map[lab[i]];
+      for (int i = tid; i < n; i += kT) P.child[row0 + i] = map[lab[i]];
     KPHASE_END(KP_RELABEL);
     if (P.centres) {
       float* co = P.centres + static_cast<long long>(s) * P.Kmax * P.Kmax;
-      for (int e = threadIdx.x; e < P.Kmax * P.Kmax; e += kThreads) co[e] = 0.f;
-      __syncthreads();
-      for (int e = threadIdx.x; e < K * K; e += kThreads) {
+      for (int e = tid; e < P.Kmax * P.Kmax; e += kT) co[e] = 0.f;
+      G::sync();
+      for (int e = tid; e < K * K; e += kT) {
         const int c = e / K, d = e % K;
         if (map[c] >= 0) co[map[c] * P.Kmax + d] = cen[c * LDC + d];
       }
     }
-    __syncthreads();
+    G::sync();
   }
 }
 
@@ -349,7 +393,7 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
       const float wt = P.weight[row0 + i];
       if (wt > bv) { bv = wt; bi = i; }
     }
-    first = block_argmax(bv, bi, w.sval, w.sidx, flip);
+    first = block_argmax<G>(bv, bi, w.sval, w.sidx, flip);
     if (first < 0 || first >= n) first = 0;
   }
   __syncthreads();
@@ -365,7 +409,7 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
       cacc[i] = c;
       if (-c > bv) { bv = -c; bi = i; }       // argmin c, ties -> lowest index
     }
-    const int nxt = block_argmax(bv, bi, w.sval, w.sidx, flip);
+    const int nxt = block_argmax<G>(bv, bi, w.sval, w.sidx, flip);
     for (int d = threadIdx.x; d < K; d += kThreads) R[d * LDC + j] = pts[d * ldp + nxt];
     __syncthreads();
   }
@@ -456,11 +500,12 @@ __device__ __forceinline__ void kway_segment(const Params& P, const Work& w, con
   __syncthreads();
 }
 
+template <class G>
 __device__ __forceinline__ void kmeans_dispatch(const Params& P, const Work& w, int s, int row0, int n, int K) {
-  if (K <= 4) kmeans_segment<4>(P, w, s, row0, n, K);
-  else if (K <= 8) kmeans_segment<8>(P, w, s, row0, n, K);
-  else if (K <= 16) kmeans_segment<16>(P, w, s, row0, n, K);
-  else kmeans_segment<32>(P, w, s, row0, n, K);
+  if (K <= 4) kmeans_segment<4, G>(P, w, s, row0, n, K);
+  else if (K <= 8) kmeans_segment<8, G>(P, w, s, row0, n, K);
+  else if (K <= 16) kmeans_segment<16, G>(P, w, s, row0, n, K);
+  else kmeans_segment<32, G>(P, w, s, row0, n, K);
 }
 
 __device__ __forceinline__ int select_k(const Params& P, const float* __restrict__ lam, int n) {
@@ -502,7 +547,7 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
     }
     __syncthreads();
     if (P.discretise == 1) kway_segment(P, w, ks, s, row0, n, K);
-    else kmeans_dispatch(P, w, s, row0, n, K);
+    else kmeans_dispatch<ThreadGroup<0, kThreads, 0>>(P, w, s, row0, n, K);
   }
 }
 
@@ -510,8 +555,13 @@ __global__ void __launch_bounds__(kThreads) kmeans_kernel(const Params P) {
 //   H_lead = W Theta W^T (Jacobi; the leading kconv columns if they converged as a block, else the whole block),
 //   V = D^1/2 U W, eigenvalues descending, canonical sign (largest-|entry| positive, ties -> lowest row), then the
 //   k-means of kmeans_kernel on the embedding that is already in shared memory.
+// Overlapped route (the usual case: fixed cluster count K = the converged leading block = all k columns): W is an
+// orthogonal K x K matrix, so the pairwise distances of the rows of D^1/2 U[:, :K] equal those of V[:, :K]; warps 0-2
+// run the k-means on the unrotated coordinates while warp 3 runs the Jacobi sweeps, and the rotation, signs and
+// eigenvector output follow when both are done.
 __global__ void __launch_bounds__(kThreads, 7) ritz_kmeans_kernel(const Params P) {
   using G = ThreadGroup<0, kThreads, 0>;
+  using KG = ThreadGroup<0, kThreads - 32, 1>;
   extern __shared__ __align__(16) float smem[];
   __shared__ float sval[2 * (kThreads / 32)];
   __shared__ int sidx[2 * (kThreads / 32)];
@@ -529,71 +579,113 @@ __global__ void __launch_bounds__(kThreads, 7) ritz_kmeans_kernel(const Params P
     const int row0 = s * n;
     __syncthreads();
     KPHASE_BEGIN();
-    // this thread's (at most two) basis rows and degrees: requested now, they land while the Jacobi sweeps run
-    float4 ur[kRitzTokens][4];
-    float dg[kRitzTokens];
-#pragma unroll
-    for (int t = 0; t < kRitzTokens; ++t) {
-      const int i = threadIdx.x + t * kThreads;
-      if (i < n) {
-        const float4* up = reinterpret_cast<const float4*>(P.U + static_cast<size_t>(row0 + i) * MB);
-        ur[t][0] = __ldg(up); ur[t][1] = __ldg(up + 1); ur[t][2] = __ldg(up + 2); ur[t][3] = __ldg(up + 3);
-        dg[t] = __ldg(P.weight + row0 + i);
-      }
-    }
     for (int e = threadIdx.x; e < MB * MB; e += kThreads) Hm[(e >> 4) * LD + (e & 15)] = P.H[static_cast<size_t>(s) * 256 + e];
-    __syncthreads();
     const int kk = P.kconv < m ? P.kconv : m;
     int md = m;
     if (P.info[s]) {
       const int mdb = (kk + 1) & ~1;
       if (mdb <= m) md = mdb;
     }
-    eig::jacobi<G>(Hm, Sm, LD, md, 12, rot);
-    KPHASE_END(KP_JACOBI);
-    if (threadIdx.x < m) {
-      const int a = threadIdx.x;
-      const float ta = Hm[a * LD + a];
-      if (a < md) {
-        int rank = 0;
-        for (int b = 0; b < md; ++b) {
-          const float tb = Hm[b * LD + b];
-          rank += (tb > ta || (tb == ta && b < a)) ? 1 : 0;
-        }
-        order[rank] = a;
-        theta[rank] = ta;
-      } else {
-        order[a] = a;
-        theta[a] = ta;
-      }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < MB * MB; e += kThreads) {
-      const int c = e >> 4, a = e & 15;
-      Wt[e] = (c < m && a < m) ? ((c < md && a < md) ? Sm[a * LD + order[c]] : (a == c ? 1.f : 0.f)) : 0.f;
-    }
-    __syncthreads();
-    // v_c(i) = sqrt(d_i) sum_a W[c][a] u_a(i), written (transposed) to the embedding
-#pragma unroll
-    for (int t = 0; t < kRitzTokens; ++t) {
-      const int i = threadIdx.x + t * kThreads;
-      if (i < n) {
-        const float sd = sqrtf(dg[t]);
-        for (int c = 0; c < k; ++c) {
-          float acc = 0.f;
-#pragma unroll
-          for (int a4 = 0; a4 < 4; ++a4) {
-            const float4 wv = *reinterpret_cast<const float4*>(Wt + c * MB + 4 * a4);
-            acc = fmaf(wv.x, ur[t][a4].x, acc);
-            acc = fmaf(wv.y, ur[t][a4].y, acc);
-            acc = fmaf(wv.z, ur[t][a4].z, acc);
-            acc = fmaf(wv.w, ur[t][a4].w, acc);
+    // eigenvalue order of the diagonalised block and the rotation Wt, by threads [0, nt) of one group
+    auto ritz_basis = [&](int t, int nt, auto&& sync) {
+      if (t < m) {
+        const int a = t;
+        const float ta = Hm[a * LD + a];
+        if (a < md) {
+          int rank = 0;
+          for (int b = 0; b < md; ++b) {
+            const float tb = Hm[b * LD + b];
+            rank += (tb > ta || (tb == ta && b < a)) ? 1 : 0;
           }
-          w.pts[c * w.ldp + i] = acc * sd;
+          order[rank] = a;
+          theta[rank] = ta;
+        } else {
+          order[a] = a;
+          theta[a] = ta;
         }
       }
+      sync();
+      for (int e = t; e < MB * MB; e += nt) {
+        const int c = e >> 4, a = e & 15;
+        Wt[e] = (c < m && a < m) ? ((c < md && a < md) ? Sm[a * LD + order[c]] : (a == c ? 1.f : 0.f)) : 0.f;
+      }
+    };
+    const bool overlap = P.discretise == 0 && P.n_clusters > 0 && !P.init && md <= 8 && k == md && P.n_clusters == md && n >= md;
+    if (overlap) {
+      // x_a(i) = sqrt(d_i) u_a(i), a < md: the k-means coordinates
+#pragma unroll
+      for (int t = 0; t < kRitzTokens; ++t) {
+        const int i = threadIdx.x + t * kThreads;
+        if (i < n) {
+          const float4* up = reinterpret_cast<const float4*>(P.U + static_cast<size_t>(row0 + i) * MB);
+          const float4 u0 = __ldg(up), u1 = __ldg(up + 1);
+          const float sd = sqrtf(__ldg(P.weight + row0 + i));
+          const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+            if (a < md) w.pts[a * w.ldp + i] = u[a] * sd;
+        }
+      }
+      __syncthreads();
+      KPHASE_END(KP_JACOBI);
+      if (warp == kThreads / 32 - 1) {
+        eig::jacobi_warp8<G>(Hm, Sm, LD, md, 12);
+        __syncwarp();
+        ritz_basis(lane, 32, [] { __syncwarp(); });
+      } else {
+        if (md <= 4) kmeans_segment<4, KG>(P, w, s, row0, n, md);
+        else kmeans_segment<8, KG>(P, w, s, row0, n, md);
+      }
+      __syncthreads();
+      // v_c(i) = sum_a W[c][a] x_a(i): a thread rotates its own tokens in place
+#pragma unroll
+      for (int t = 0; t < kRitzTokens; ++t) {
+        const int i = threadIdx.x + t * kThreads;
+        if (i < n) {
+          float x[8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) x[a] = a < md ? w.pts[a * w.ldp + i] : 0.f;
+          for (int c = 0; c < k; ++c) {
+            const float4 w0 = *reinterpret_cast<const float4*>(Wt + c * MB);
+            const float4 w1 = *reinterpret_cast<const float4*>(Wt + c * MB + 4);
+            float acc = w0.x * x[0];
+            acc = fmaf(w0.y, x[1], acc); acc = fmaf(w0.z, x[2], acc); acc = fmaf(w0.w, x[3], acc);
+            acc = fmaf(w1.x, x[4], acc); acc = fmaf(w1.y, x[5], acc); acc = fmaf(w1.z, x[6], acc); acc = fmaf(w1.w, x[7], acc);
+            w.pts[c * w.ldp + i] = acc;
+          }
+        }
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      eig::jacobi<G>(Hm, Sm, LD, md, 12, rot);
+      KPHASE_END(KP_JACOBI);
+      ritz_basis(static_cast<int>(threadIdx.x), kThreads, [] { __syncthreads(); });
+      __syncthreads();
+      // v_c(i) = sqrt(d_i) sum_a W[c][a] u_a(i), written (transposed) to the embedding
+#pragma unroll
+      for (int t = 0; t < kRitzTokens; ++t) {
+        const int i = threadIdx.x + t * kThreads;
+        if (i < n) {
+          const float4* up = reinterpret_cast<const float4*>(P.U + static_cast<size_t>(row0 + i) * MB);
+          const float4 ur[4] = {__ldg(up), __ldg(up + 1), __ldg(up + 2), __ldg(up + 3)};
+          const float sd = sqrtf(__ldg(P.weight + row0 + i));
+          for (int c = 0; c < k; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int a4 = 0; a4 < 4; ++a4) {
+              const float4 wv = *reinterpret_cast<const float4*>(Wt + c * MB + 4 * a4);
+              acc = fmaf(wv.x, ur[a4].x, acc);
+              acc = fmaf(wv.y, ur[a4].y, acc);
+              acc = fmaf(wv.z, ur[a4].z, acc);
+              acc = fmaf(wv.w, ur[a4].w, acc);
+            }
+            w.pts[c * w.ldp + i] = acc * sd;
+          }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // canonical sign per column (one warp per column), eigenvalues
     for (int c = warp; c < k; c += kThreads / 32) {
       float best = -1.f, bval = 0.f;
@@ -631,29 +723,32 @@ __global__ void __launch_bounds__(kThreads, 7) ritz_kmeans_kernel(const Params P
             x.y = w.pts[(c + 1) * w.ldp + i] * sgn[c + 1];
             x.z = w.pts[(c + 2) * w.ldp + i] * sgn[c + 2];
             x.w = w.pts[(c + 3) * w.ldp + i] * sgn[c + 3];
-            w.pts[c * w.ldp + i] = x.x;
-            w.pts[(c + 1) * w.ldp + i] = x.y;
-            w.pts[(c + 2) * w.ldp + i] = x.z;
-            w.pts[(c + 3) * w.ldp + i] = x.w;
+            if (!overlap) {
+              w.pts[c * w.ldp + i] = x.x;
+              w.pts[(c + 1) * w.ldp + i] = x.y;
+              w.pts[(c + 2) * w.ldp + i] = x.z;
+              w.pts[(c + 3) * w.ldp + i] = x.w;
+            }
             *reinterpret_cast<float4*>(vo + c) = x;
           }
         } else {
           for (int c = 0; c < k; ++c) {
             const float x = w.pts[c * w.ldp + i] * sgn[c];
-            w.pts[c * w.ldp + i] = x;
+            if (!overlap) w.pts[c * w.ldp + i] = x;
             vo[c] = x;
           }
         }
       }
     }
+    KPHASE_END(KP_ROTATE);
+    if (overlap) continue;
     __syncthreads();
     const int K = select_k(P, lam_s, n);
-    KPHASE_END(KP_ROTATE);
     if (P.discretise == 1) {
       const KwayScratch ks{Hm, Sm, Wm, rot};   // the Ritz step is done with them
       kway_segment(P, w, ks, s, row0, n, K);
     } else {
-      kmeans_dispatch(P, w, s, row0, n, K);
+      kmeans_dispatch<G>(P, w, s, row0, n, K);
     }
   }
 }

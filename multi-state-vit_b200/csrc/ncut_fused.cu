@@ -27,6 +27,7 @@
 // k-loop, then epilogue and eigensolver (thread = token row; warps 2 and 6 also issue the TS-form MMAs of their tile).
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "eig_core.cuh"
@@ -745,8 +746,7 @@ extern "C" int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U
 
   const size_t fixed = 1024 + kUopBytes + ((sizeof(Shared) + 15) & ~size_t(15)) +
                        static_cast<size_t>(make_eig_layout().total) * sizeof(float);
-  size_t kMaxSmem = 227 * 1024;
-  if (const char* rs = getenv("MSVIT_FUSED_RESERVE_KB")) kMaxSmem -= static_cast<size_t>(atoi(rs)) * 1024;   // development
+  const size_t kMaxSmem = 227 * 1024;
   int stages = static_cast<int>((kMaxSmem - fixed) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return MSVIT_ERR_SHAPE;

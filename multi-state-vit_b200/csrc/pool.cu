@@ -8,6 +8,8 @@
 // accumulating in registers -- no atomics, coalesced 128-bit loads, one store per (cluster, column).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace msvit {

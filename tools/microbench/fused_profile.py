@@ -52,6 +52,15 @@ def run(argv):
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     print(f"fused kernel median {ts[len(ts)//2]:.4f} ms min {ts[0]:.4f}; iters mean {iters.float().mean():.2f} max {int(iters.max())} converged {int(info.sum())}/{B}")
+    # load balance of the static segment -> CTA map against in-order dynamic dispatch (cost model: 42k + 8k * iterations)
+    import heapq
+    it = iters.cpu().tolist(); G = min(B, 148)
+    cost = [42.0 + 8.0 * v for v in it]
+    static = [sum(cost[c::G]) for c in range(G)]
+    heap = [0.0] * G
+    for c in cost:
+        heapq.heappush(heap, heapq.heappop(heap) + c)
+    print(f"k-cycles per CTA: static mean {sum(static) / G:.0f} max {max(static):.0f}; dynamic dispatch makespan {max(heap):.0f}")
     names = ["gram", "epilogue", "init", "uop", "product", "drain", "grams", "trigger", "chol", "subst", "output", "x1_cholesky_warp", "x2_ybar_wait"]
     buf = (ctypes.c_ulonglong * len(names))()
     lib.msvit_fused_profile(buf, 1)
