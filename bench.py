@@ -156,12 +156,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(N, D, K, k, n_images: int, batch: int = 8):
-    """Times the CPU oracle (torch CPU restatement, all host threads) on `n_images` images of the workload,
-    processed in batches of `batch` (BASELINE.json configs[0] is batch 8).  Returns (images/s, cores, seconds)."""
+def cpu_oracle_rate(N, D, K, k, n_images: int, batch: int = 8, threads=None):
+    """Times the CPU oracle (torch CPU restatement, all host threads unless `threads` says otherwise) on `n_images`
+    images of the workload, processed in batches of `batch` (BASELINE.json configs[0] is batch 8).
+    Returns (images/s, threads, seconds, images)."""
     from oracle import ncut_oracle as O
     from msvit.synthetic import default_scale, planted_tokens
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     pool_n = min(n_images, 64)
     x, _ = planted_tokens(pool_n, N, D, K)
@@ -180,6 +181,61 @@ def cpu_oracle_rate(N, D, K, k, n_images: int, batch: int = 8):
         done += one((done % pool_n) // batch * batch if pool_n >= batch else 0)
     dt = time.perf_counter() - t0
     return done / dt, torch.get_num_threads(), dt, done
+
+
+def torch_cuda_eager_rate(N, D, K, k, n_images: int, dev, gamma=3.0):
+    """BASELINE.md section 3's extra reference row: the reference path's arithmetic as plain eager torch on the GPU
+    (cuBLAS matmul + elementwise exp + cuSOLVER eigh + eager k-means + one-hot matmul pooling), fp32, CUDA-event
+    timed.  None of this repo's kernels run here.  Returns (images/s, ms)."""
+    from msvit.synthetic import default_scale, planted_tokens
+    x, _ = planted_tokens(min(n_images, 64), N, D, K)
+    x = x.repeat((n_images + x.shape[0] - 1) // x.shape[0], 1, 1)[:n_images].to(dev)
+    scale = default_scale(D)
+
+    def step():
+        sq = (x * x).sum(-1)
+        d2 = (sq[:, :, None] + sq[:, None, :] - 2.0 * torch.bmm(x, x.transpose(1, 2))).clamp_min(0) / scale
+        A = torch.exp(-d2 / gamma)
+        deg = A.sum(-1)
+        dis = deg.rsqrt()
+        lam, vec = torch.linalg.eigh(A * dis[:, :, None] * dis[:, None, :])
+        V = vec[:, :, -k:].flip(-1)[:, :, :K]                      # leading eigenvectors, descending
+        # farthest-point seeding + Lloyd, batched
+        first = deg.argmax(1)
+        bidx = torch.arange(x.shape[0], device=dev)
+        cen = V[bidx, first][:, None, :]
+        mind = ((V - cen) ** 2).sum(-1)
+        for _ in range(1, K):
+            nxt = mind.argmax(1)
+            c = V[bidx, nxt][:, None, :]
+            cen = torch.cat([cen, c], 1)
+            mind = torch.minimum(mind, ((V - c) ** 2).sum(-1))
+        lab = None
+        for _ in range(20):
+            new = torch.cdist(V, cen).argmin(-1)
+            if lab is not None and torch.equal(new, lab):
+                break
+            lab = new
+            oh = torch.nn.functional.one_hot(lab, K).to(V.dtype)
+            cnt = oh.sum(1)
+            cen = torch.where(cnt[:, :, None] > 0, torch.bmm(oh.transpose(1, 2), V) / cnt.clamp_min(1)[:, :, None], cen)
+        oh = torch.nn.functional.one_hot(lab, K).to(x.dtype)
+        pooled = torch.bmm(oh.transpose(1, 2), x) / oh.sum(1).clamp_min(1)[:, :, None]
+        return pooled
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[1]
+    return n_images / ms * 1e3, ms
 
 
 def run_reference(args):
@@ -424,6 +480,18 @@ def run_ours(args):
     }
     if extras:
         line["extra_configs"] = extras
+    if rank == 0 and args.extras:
+        # the single-thread CPU row and the plain torch-CUDA row, beside cpu_baseline
+        r1, _, s1, n1 = cpu_oracle_rate(N, D, K, k, max(8, args.cpu_images // 32), threads=1)
+        n_eager = min(B, 256)
+        re, ms_e = torch_cuda_eager_rate(N, D, K, k, n_eager, dev)
+        line["extra_baselines"] = {
+            "cpu_oracle_1_thread": {"value": round(r1, 2), "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{n1} images of {args.config} in batches of 8 ({s1:.1f} s)"},
+            "torch_cuda_eager": {"value": round(re, 1), "unit": UNIT, "kind": "plain torch on 1 B200 (cuBLAS bmm, exp, "
+                                 "cuSOLVER eigh, eager k-means, one-hot bmm pooling), fp32, none of this repo's kernels",
+                                 "sample": f"{n_eager} images of {args.config} in one batch, median of 3 ({ms_e:.1f} ms)"},
+        }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
