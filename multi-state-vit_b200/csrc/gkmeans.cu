@@ -247,31 +247,44 @@ __global__ void __launch_bounds__(128) hist_kernel(const int32_t* __restrict__ l
   for (int c = threadIdx.x; c < k; c += blockDim.x) hist[static_cast<size_t>(b) * k + c] = cnt[c];
 }
 
-// Offsets of the blocks inside each label, many CTAs: one thread per label walks the blocks (eight independent loads
-// at a time), hist[b][c] <- number of rows of label c in the blocks before b, tot[c] = the label's row count.
-// The workspace holds the label totals behind the histograms.
-__global__ void __launch_bounds__(64) block_offsets_kernel(int32_t* __restrict__ hist, int nb, int k,
-                                                          int32_t* __restrict__ tot) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= k) return;
+// Offsets of the blocks inside each label: hist[b][c] <- number of rows of label c in the blocks before b, tot[c] = the
+// label's row count (the workspace holds the totals behind the histograms).  A CTA owns 32 labels (lane = label, so
+// every load is one 128-byte line) and cuts the blocks into one chunk per warp: chunk sums, a scan of the 16 sums per
+// label in shared memory, then the running offsets -- two short passes instead of one walk over all the blocks.
+constexpr int kOffWarps = 16;
+__global__ void __launch_bounds__(32 * kOffWarps) block_offsets_kernel(int32_t* __restrict__ hist, int nb, int k,
+                                                                       int32_t* __restrict__ tot) {
+  __shared__ int32_t part[kOffWarps][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int chunk = (nb + kOffWarps - 1) / kOffWarps;
+  const int b0 = min(nb, warp * chunk), b1 = min(nb, b0 + chunk);
+  int sum = 0;
+  if (c < k)
+    for (int b = b0; b < b1; ++b) sum += hist[static_cast<size_t>(b) * k + c];
+  part[warp][lane] = sum;
+  __syncthreads();
   int run = 0;
-  int b = 0;
-  for (; b + 8 <= nb; b += 8) {
-    int v[8];
+  for (int w = 0; w < warp; ++w) run += part[w][lane];
+  if (c < k) {
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      int v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = hist[static_cast<size_t>(b + i) * k + c];
+      for (int i = 0; i < 8; ++i) v[i] = hist[static_cast<size_t>(b + i) * k + c];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      hist[static_cast<size_t>(b + i) * k + c] = run;
-      run += v[i];
+      for (int i = 0; i < 8; ++i) {
+        hist[static_cast<size_t>(b + i) * k + c] = run;
+        run += v[i];
+      }
     }
+    for (; b < b1; ++b) {
+      const int v = hist[static_cast<size_t>(b) * k + c];
+      hist[static_cast<size_t>(b) * k + c] = run;
+      run += v;
+    }
+    if (warp == kOffWarps - 1) tot[c] = run;
   }
-  for (; b < nb; ++b) {
-    const int v = hist[static_cast<size_t>(b) * k + c];
-    hist[static_cast<size_t>(b) * k + c] = run;
-    run += v;
-  }
-  tot[c] = run;
 }
 
 // seg_off = exclusive scan of the label totals (one CTA, 1024 labels per pass)
@@ -569,7 +582,7 @@ extern "C" int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* 
   const size_t smem = static_cast<size_t>(k) * sizeof(int32_t);
   if (nb > 0) hist_kernel<<<nb, 128, smem, stream>>>(labels, static_cast<int>(n), k, hist);
   int32_t* tot = hist + static_cast<size_t>(nb > 0 ? nb : 1) * k;
-  block_offsets_kernel<<<ceil_div(k, 64), 64, 0, stream>>>(hist, nb, k, tot);
+  block_offsets_kernel<<<ceil_div(k, 32), 32 * kOffWarps, 0, stream>>>(hist, nb, k, tot);
   label_scan_kernel<<<1, 1024, 0, stream>>>(tot, k, seg_off);
   if (nb > 0) scatter_kernel<<<nb, 32, smem, stream>>>(labels, static_cast<int>(n), k, hist, seg_off, perm);
   return cuda_status(cudaGetLastError());

@@ -157,6 +157,38 @@ __global__ void __launch_bounds__(256) key_sums_kernel(const float* __restrict__
 // size (receiver row).  Every attention element is loaded once: B*H*N*N*4 bytes read, (2 C / N) of that written.
 constexpr int kStatsChunks = 8;   // per-lane register chunks along the key axis: N <= 32 * 8 * VEC
 
+// Sum CMAX per-lane values over the warp with a transposing butterfly: at offsets 16, 8, ... a lane keeps one half of
+// its live values and hands the other half to its partner, so the 5 steps cost CMAX - 1 (+ the steps left once a
+// single value remains) shuffles instead of 5 CMAX.  On return acc[i], i < R, of lane l holds the total of column
+// (l >> (5 - H)) * R + i, with H = min(5, log2 CMAX) and R = CMAX >> H.
+template <int CMAX>
+struct ColumnReduce {
+  static constexpr int H = CMAX >= 32 ? 5 : (CMAX == 16 ? 4 : (CMAX == 8 ? 3 : (CMAX == 4 ? 2 : 1)));
+  static constexpr int R = CMAX >> H;
+  static __device__ __forceinline__ int column(int lane, int i) { return (lane >> (5 - H)) * R + i; }
+  static __device__ __forceinline__ bool writer(int lane) { return (lane & ((1 << (5 - H)) - 1)) == 0; }
+  template <int N, int O>
+  static __device__ __forceinline__ void step(float (&acc)[CMAX], int lane) {
+    if constexpr (O >= 1) {
+      if constexpr (N > R) {
+        const bool up = (lane & O) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+          const float keep = up ? acc[i + N / 2] : acc[i];
+          const float give = up ? acc[i] : acc[i + N / 2];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, give, O);
+        }
+        step<N / 2, O / 2>(acc, lane);
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], O);
+        step<N, O / 2>(acc, lane);
+      }
+    }
+  }
+  static __device__ __forceinline__ void run(float (&acc)[CMAX], int lane) { step<CMAX, 16>(acc, lane); }
+};
+
 template <int CMAX, int VEC>
 __device__ __forceinline__ void stats_row(const float* __restrict__ row, const int* lab, int N, int lane,
                                           float (&acc)[CMAX], float (&col)[kStatsChunks][VEC]) {
@@ -182,10 +214,19 @@ __device__ __forceinline__ void stats_row(const float* __restrict__ row, const i
       }
     }
   }
+  ColumnReduce<CMAX>::run(acc, lane);
+}
+
+// the transmitter row of query q from the reduced accumulators (see ColumnReduce for who holds what)
+template <int CMAX>
+__device__ __forceinline__ void store_key_sums(float* __restrict__ o, const float (&acc)[CMAX], int lane, int C) {
+  using CR = ColumnReduce<CMAX>;
+  if (CR::writer(lane)) {
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    for (int i = 0; i < CR::R; ++i) {
+      const int c = CR::column(lane, i);
+      if (c < C) o[c] = acc[i];
+    }
   }
 }
 
@@ -221,9 +262,7 @@ __global__ void __launch_bounds__(256) attention_stats_kernel(const float* __res
       const int q = order[i];
       stats_row<CMAX, VEC>(base + static_cast<size_t>(q) * N, lab, N, lane, acc, col);
       float* o = tr + (static_cast<size_t>(bh) * N + q) * C;
-#pragma unroll
-      for (int cc = 0; cc < CMAX; ++cc)
-        if (lane == (cc & 31) && cc < C) o[cc] = acc[cc];
+      store_key_sums<CMAX>(o, acc, lane, C);
     }
 #pragma unroll
     for (int j = 0; j < kStatsChunks; ++j) {
@@ -248,9 +287,7 @@ __global__ void __launch_bounds__(256) attention_stats_kernel(const float* __res
       if (lab[q] >= 0) continue;
       stats_row<CMAX, VEC>(base + static_cast<size_t>(q) * N, lab, N, lane, acc, col);
       float* o = tr + (static_cast<size_t>(bh) * N + q) * C;
-#pragma unroll
-      for (int cc = 0; cc < CMAX; ++cc)
-        if (lane == (cc & 31) && cc < C) o[cc] = acc[cc];
+      store_key_sums<CMAX>(o, acc, lane, C);
     }
   }
 }
