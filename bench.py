@@ -377,6 +377,26 @@ def run_ours(args):
                     "d2h_bytes_per_step": hc.d2h_bytes, "ms_per_step": round(ms16 / e2e_steps, 3),
                     "labels_equal_fp32_run": bool(torch.equal(res16.labels, res.labels))}
         del host16
+        # device-resident step with bf16 tokens (north_star's "TMA-staged bf16 tiles"): kind::f16 Gram, half the bytes
+        x16 = x.to(torch.bfloat16)
+        plan16 = ClusterPlan(B, N, D, torch.bfloat16, dev, ncut_dim=k, n_clusters=K, scale=scale)
+        for _ in range(args.warmup):
+            out16 = plan16.run(x16)
+        ev16 = [[torch.cuda.Event(enable_timing=True) for _ in range(n_st + 1)] for _ in range(args.steps)]
+        barrier()
+        b0_.record()
+        for s in range(args.steps):
+            out16 = plan16.run(x16, events=ev16[s])
+        b1_.record()
+        barrier()
+        ms16d = reduce_max(b0_.elapsed_time(b1_)) / args.steps
+        e2e_bf16["device_resident"] = {
+            "value": round(world * B / ms16d * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms16d, 4),
+            "stages_ms": {name: round(sum(ev[i].elapsed_time(ev[i + 1]) for ev in ev16) / args.steps, 4)
+                          for i, name in enumerate(ClusterPlan.STAGES) if any(ev[i].elapsed_time(ev[i + 1]) > 0 for ev in ev16)},
+            "labels_equal_fp32_run": bool(torch.equal(out16.labels, out.labels)),
+            "note": "same step as `value` with the tokens held in bf16 on the device"}
+        del x16, plan16, out16
 
     # ---- the other BASELINE.json configs as sub-records (C3, C4 with its three levels, C5 with its NCCL all-reduce)
     extras = {}
@@ -503,10 +523,15 @@ def extra_per_image(name, dev, world, rank, steps, warmup, barrier, reduce_max):
     every parent segment re-clustered into 4 children from that level's hidden states) as sub-records of the main
     line: device-resident images/s per GPU batch, weak scaling, per-stage ms."""
     from msvit.functional import ClusterPlan
-    from msvit.synthetic import default_scale, planted_tokens
+    from msvit.synthetic import default_scale, hierarchical_tokens, planted_tokens
     B, N, D, K, k = workload(name)
     pool_n = min(B, 32)
-    xs, _ = planted_tokens(pool_n, N, D, K, first=rank * pool_n)
+    if name == "C4":
+        # a planted 4 x 4 x 4 tree: every level of re-clustering has four sub-clusters to find (a flat mixture makes
+        # levels 1 and 2 cluster iid noise, which only measures the iteration cap)
+        xs, _ = hierarchical_tokens(pool_n, N, D, branch=K, depth=3, first=rank * pool_n)
+    else:
+        xs, _ = planted_tokens(pool_n, N, D, K, first=rank * pool_n)
     x = xs.repeat((B + pool_n - 1) // pool_n, 1, 1)[:B].contiguous().to(dev)
     scale = default_scale(D)
     if name != "C4":
@@ -549,7 +574,7 @@ def extra_per_image(name, dev, world, rank, steps, warmup, barrier, reduce_max):
                 stage_ms[nm if len(plans) == 1 else f"L{l}.{nm}"] = round(v, 4)
     rec = {"value": round(world * B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "scaling": "weak",
            "workload": workload_string(name, B, N, D, K, k, "float32") +
-                       (" -- 3 hierarchical levels (1, 4, 16 parents per image)" if name == "C4" else ""),
+                       (" -- 3 hierarchical levels (1, 4, 16 parents per image), tokens from a planted 4x4x4 tree" if name == "C4" else ""),
            "stages_ms": stage_ms, "eig_iters_mean": [round(float(o.iters.float().mean()), 2) for o in outs],
            "converged": [bool(o.converged.all()) for o in outs]}
     if name == "C4":

@@ -105,10 +105,10 @@ static int launch(const void* x, const int64_t* labels, float* pooled, int32_t* 
   const int ysplit = ceil_div(cols, threads);
   const size_t smem = sizeof(int) * (2 * static_cast<size_t>(N) + 2 * static_cast<size_t>(K) + 1);
   if (smem > 200 * 1024) return MSVIT_ERR_SHAPE;
-  // fewer than 4 CTAs per SM: split the clusters for 8 per SM, at most 8 ranges (each CTA repeats the grouping)
-  const long long ctas = static_cast<long long>(B) * ysplit;
-  const int sms = sm_count();
-  long long zsplit = ctas >= 4LL * sms ? 1 : (8LL * sms + ctas - 1) / ctas;
+  // fewer than 1024 threads per SM: split the clusters over more CTAs, at most 8 ranges (each CTA repeats the grouping)
+  const long long total_threads = static_cast<long long>(B) * ysplit * threads;
+  const long long want_threads = 1024LL * sm_count();
+  long long zsplit = (want_threads + total_threads - 1) / total_threads;
   if (zsplit > 8) zsplit = 8;
   if (zsplit > K) zsplit = K;
   if (zsplit < 1) zsplit = 1;

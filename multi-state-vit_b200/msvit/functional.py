@@ -28,8 +28,15 @@ class ClusterOutput:
     n_child: torch.Tensor           # [B, P] int32 children per parent
     degree: torch.Tensor            # [B, N] fp32 NCut degree
     iters: torch.Tensor             # [B, P] int32 eigensolver iterations
-    converged: torch.Tensor         # [B, P] bool: the wanted eigenpairs met the residual tolerance before the iteration cap
     affinity: Optional[torch.Tensor] = None  # [B, N, N] fp32 (single-parent case with N % 4 == 0 only)
+    verdict: Optional[torch.Tensor] = None   # [B, P] int32, fused path: 1 = the leading block met the tolerance
+    iter_cap: int = 0                        # two-kernel path: the iteration cap (stopping there = not converged)
+
+    @property
+    def converged(self) -> torch.Tensor:
+        """[B, P] bool: the wanted eigenpairs met the residual tolerance before the iteration cap.  Derived on demand
+        (one small elementwise kernel), so a caller that never asks pays nothing per step."""
+        return (self.verdict == 1) if self.verdict is not None else (self.iters < self.iter_cap)
 
 
 FUSED_BLOCK = 16     # subspace width of the fused kernel
@@ -261,11 +268,10 @@ class ClusterPlan:
             V_tok, deg_tok = self.V, self.deg
         aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0 and not self.fused) else None
         # the fused kernel reports its verdict; the two-kernel solver stops at the cap only when it did not converge
-        conv = (self.info == 1) if self.fused else (self.iters < self.eig_iters)
         return ClusterOutput(labels=self.child, pooled=self.pooled, counts=self.counts, eigvecs=V_tok.view(B, N, k),
                              eigvals=self.lam.view(B, P, k), n_child=self.n_child.view(B, P),
-                             degree=deg_tok.view(B, N), iters=self.iters.view(B, P), converged=conv.view(B, P),
-                             affinity=aff)
+                             degree=deg_tok.view(B, N), iters=self.iters.view(B, P), affinity=aff,
+                             verdict=self.info.view(B, P) if self.fused else None, iter_cap=self.eig_iters)
 
 
 def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, *, ncut_dim: int,

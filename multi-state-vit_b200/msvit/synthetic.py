@@ -53,6 +53,40 @@ def planted_tokens(B: int, N: int, D: int, K: int, noise: float = 0.5, seed: int
     return x, lab
 
 
+def hierarchical_image(b: int, N: int, D: int, branch: int = 4, depth: int = 3, spread=(1.0, 0.7, 0.5),
+                       noise: float = 0.3, seed: int = 1212) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Image `b` of the hierarchical workload (C4): a planted tree of `depth` levels with `branch` children per node.
+    A node's centre is its parent's centre + spread[level] * randn(D); a token is its leaf's centre + noise * randn(D).
+    Children of a node have unequal sizes (proportional to branch + c), exact rather than sampled.  Re-clustering a
+    level-l cluster therefore has `branch` sub-clusters to find, which a flat mixture does not offer.
+    Returns (x [N, D] fp32, leaf ids [N] int64 in [0, branch**depth))."""
+    g = torch.Generator().manual_seed(seed + b)
+    centres = torch.zeros(1, D)
+    sizes = torch.tensor([N])
+    w = torch.arange(branch, 2 * branch, dtype=torch.float64)
+    for level in range(depth):
+        centres = (centres[:, None, :] + spread[level] * torch.randn(centres.shape[0], branch, D, generator=g)).reshape(-1, D)
+        new = []
+        for n_node in sizes.tolist():
+            sz = torch.floor(w / w.sum() * n_node).long()
+            sz[branch - 1] += n_node - int(sz.sum())
+            new.append(sz)
+        sizes = torch.cat(new)
+    leaf = torch.repeat_interleave(torch.arange(centres.shape[0]), sizes)[torch.randperm(N, generator=g)]
+    x = centres[leaf] + noise * torch.randn(N, D, generator=g)
+    return x, leaf
+
+
+def hierarchical_tokens(B: int, N: int, D: int, branch: int = 4, depth: int = 3, seed: int = 1212, first: int = 0
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Images first .. first+B-1 of the hierarchical workload -> (x [B, N, D] fp32, leaf ids [B, N])."""
+    x = torch.empty(B, N, D)
+    leaf = torch.empty(B, N, dtype=torch.long)
+    for i in range(B):
+        x[i], leaf[i] = hierarchical_image(first + i, N, D, branch, depth, seed=seed)
+    return x, leaf
+
+
 def planted_features(n: int, D: int, k: int, noise: float = 0.5, seed: int = 1212, first: int = 0,
                      chunk: int = 65536) -> torch.Tensor:
     """Rows first .. first+n-1 of the dataset-level (DeepCluster-style) workload: centres[lab] + noise."""
