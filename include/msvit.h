@@ -196,8 +196,8 @@ int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_indices, fl
  *   transmitter[b, h, q, c] = sum over the keys k of cluster c of attn[b, h, q, k]            [B, H, N, C]
  *   receiver[b, h, c, k]    = mean over the queries q of cluster c of attn[b, h, q, k]        [B, H, C, N]
  * (an empty cluster gives a receiver row of 0 where the reference's 0/0 gives NaN).  attn fp32, 16-byte aligned;
- * C <= 64; N <= 1024 when N is a multiple of 4, else N <= 256 -- MSVIT_ERR_SHAPE beyond that (use
- * msvit_cluster_key_sums + msvit_pool there). */
+ * N <= 256 and C <= 16 (the range where one pass beats two) -- MSVIT_ERR_SHAPE beyond that: use
+ * msvit_cluster_key_sums + msvit_pool there (C <= 64, any N). */
 int msvit_cluster_attention_stats(const float* attn, const int64_t* cluster_indices, float* transmitter,
                                   float* receiver, int B, int H, int N, int C, msvit_stream_t stream);
 

@@ -189,29 +189,44 @@ struct ColumnReduce {
   static __device__ __forceinline__ void run(float (&acc)[CMAX], int lane) { step<CMAX, 16>(acc, lane); }
 };
 
-template <int CMAX, int VEC>
-__device__ __forceinline__ void stats_row(const float* __restrict__ row, const int* lab, int N, int lane,
-                                          float (&acc)[CMAX], float (&col)[kStatsChunks][VEC]) {
+// One attention row in registers: lane l holds the VEC keys starting at (32 j + l) VEC, j < NCH (0 beyond N).
+template <int VEC, int NCH>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int N, int lane, float (&v)[NCH][VEC]) {
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int k = (j * 32 + lane) * VEC;
+    if constexpr (VEC == 4) {
+      const float4 a = k < N ? __ldcs(reinterpret_cast<const float4*>(row + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+    } else {
+      v[j][0] = k < N ? __ldcs(row + k) : 0.f;
+    }
+  }
+}
+
+// key sums of the row per cluster (reduced over the warp, see ColumnReduce) and the row added to the column sums
+template <int CMAX, int VEC, int NCH>
+__device__ __forceinline__ void stats_row(const float (&v)[NCH][VEC], const int* lab, int N, int lane,
+                                          float (&acc)[CMAX], float (&col)[NCH][VEC]) {
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
 #pragma unroll
-  for (int j = 0; j < kStatsChunks; ++j) {
+  for (int j = 0; j < NCH; ++j) {
     const int k = (j * 32 + lane) * VEC;
     if (k < N) {
       if constexpr (VEC == 4) {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(row + k));
         const int4 l = *reinterpret_cast<const int4*>(lab + k);
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          acc[c] += (l.x == c ? a.x : 0.f) + (l.y == c ? a.y : 0.f) + (l.z == c ? a.z : 0.f) + (l.w == c ? a.w : 0.f);
-        col[j][0] += a.x; col[j][1] += a.y; col[j][2] += a.z; col[j][3] += a.w;
+          acc[c] += (l.x == c ? v[j][0] : 0.f) + (l.y == c ? v[j][1] : 0.f) + (l.z == c ? v[j][2] : 0.f) +
+                    (l.w == c ? v[j][3] : 0.f);
       } else {
-        const float a = __ldcs(row + k);
         const int l = lab[k];
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) acc[c] += l == c ? a : 0.f;
-        col[j][0] += a;
+        for (int c = 0; c < CMAX; ++c) acc[c] += l == c ? v[j][0] : 0.f;
       }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) col[j][e] += v[j][e];
     }
   }
   ColumnReduce<CMAX>::run(acc, lane);
@@ -230,7 +245,9 @@ __device__ __forceinline__ void store_key_sums(float* __restrict__ o, const floa
   }
 }
 
-template <int CMAX, int VEC>
+// NCH = register chunks per row: 2 (rows of at most 64 VEC keys, the usual 196 / 256-token case; the next row of the
+// warp is requested before the current one is reduced, two rows in flight per warp) or 8 (no prefetch).
+template <int CMAX, int VEC, int NCH>
 __global__ void __launch_bounds__(256) attention_stats_kernel(const float* __restrict__ attn,
                                                               const int64_t* __restrict__ cluster_indices,
                                                               float* __restrict__ tr, float* __restrict__ rc, int H,
@@ -250,22 +267,37 @@ __global__ void __launch_bounds__(256) attention_stats_kernel(const float* __res
   const int c0 = static_cast<int>(static_cast<long long>(blockIdx.x) * C / gridDim.x);
   const int c1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * C / gridDim.x);
   const float* base = attn + static_cast<size_t>(bh) * N * N;
+  constexpr bool kPrefetch = NCH <= 2;
   float acc[CMAX];
-  float col[kStatsChunks][VEC];
+  float col[NCH][VEC];
+  float cur[NCH][VEC];
+  float nxt[kPrefetch ? NCH : 1][VEC];
   for (int c = c0; c < c1; ++c) {
     const int s0 = start[c], s1 = start[c + 1];
 #pragma unroll
-    for (int j = 0; j < kStatsChunks; ++j)
+    for (int j = 0; j < NCH; ++j)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) col[j][v] = 0.f;
-    for (int i = s0 + warp; i < s1; i += nwarps) {
+    int i = s0 + warp;
+    if (kPrefetch && i < s1) load_row<VEC, NCH>(base + static_cast<size_t>(order[i]) * N, N, lane, cur);
+    for (; i < s1; i += nwarps) {
       const int q = order[i];
-      stats_row<CMAX, VEC>(base + static_cast<size_t>(q) * N, lab, N, lane, acc, col);
-      float* o = tr + (static_cast<size_t>(bh) * N + q) * C;
-      store_key_sums<CMAX>(o, acc, lane, C);
+      if constexpr (kPrefetch) {
+        if (i + nwarps < s1) load_row<VEC, NCH>(base + static_cast<size_t>(order[i + nwarps]) * N, N, lane, nxt);
+      } else {
+        load_row<VEC, NCH>(base + static_cast<size_t>(q) * N, N, lane, cur);
+      }
+      stats_row<CMAX, VEC, NCH>(cur, lab, N, lane, acc, col);
+      store_key_sums<CMAX>(tr + (static_cast<size_t>(bh) * N + q) * C, acc, lane, C);
+      if constexpr (kPrefetch) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) cur[j][v] = nxt[j][v];
+      }
     }
 #pragma unroll
-    for (int j = 0; j < kStatsChunks; ++j) {
+    for (int j = 0; j < NCH; ++j) {
       const int k = (j * 32 + lane) * VEC;
       if (k < N) {
 #pragma unroll
@@ -285,14 +317,14 @@ __global__ void __launch_bounds__(256) attention_stats_kernel(const float* __res
   if (blockIdx.x == 0) {
     for (int q = warp; q < N; q += nwarps) {
       if (lab[q] >= 0) continue;
-      stats_row<CMAX, VEC>(base + static_cast<size_t>(q) * N, lab, N, lane, acc, col);
-      float* o = tr + (static_cast<size_t>(bh) * N + q) * C;
-      store_key_sums<CMAX>(o, acc, lane, C);
+      load_row<VEC, NCH>(base + static_cast<size_t>(q) * N, N, lane, cur);
+      stats_row<CMAX, VEC, NCH>(cur, lab, N, lane, acc, col);
+      store_key_sums<CMAX>(tr + (static_cast<size_t>(bh) * N + q) * C, acc, lane, C);
     }
   }
 }
 
-template <int CMAX, int VEC>
+template <int CMAX, int VEC, int NCH>
 static int launch_stats(const float* attn, const int64_t* ci, float* tr, float* rc, int B, int H, int N, int C,
                         cudaStream_t stream) {
   const int N4 = (N + 3) & ~3;
@@ -302,21 +334,19 @@ static int launch_stats(const float* attn, const int64_t* ci, float* tr, float* 
   if (z > 8) z = 8;
   if (z > C) z = C;
   if (z < 1) z = 1;
-  cudaError_t e = cudaFuncSetAttribute(attention_stats_kernel<CMAX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(attention_stats_kernel<CMAX, VEC, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_status(e);
-  attention_stats_kernel<CMAX, VEC><<<dim3(static_cast<unsigned>(z), B * H), 256, smem, stream>>>(attn, ci, tr, rc, H,
+  attention_stats_kernel<CMAX, VEC, NCH><<<dim3(static_cast<unsigned>(z), B * H), 256, smem, stream>>>(attn, ci, tr, rc, H,
                                                                                                 N, C);
   return cuda_status(cudaGetLastError());
 }
 
-template <int VEC>
+template <int VEC, int NCH>
 static int dispatch_stats(const float* attn, const int64_t* ci, float* tr, float* rc, int B, int H, int N, int C,
                           cudaStream_t stream) {
-  if (C <= 8) return launch_stats<8, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
-  if (C <= 16) return launch_stats<16, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
-  if (C <= 32) return launch_stats<32, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
-  return launch_stats<64, VEC>(attn, ci, tr, rc, B, H, N, C, stream);
+  if (C <= 8) return launch_stats<8, VEC, NCH>(attn, ci, tr, rc, B, H, N, C, stream);
+  return launch_stats<16, VEC, NCH>(attn, ci, tr, rc, B, H, N, C, stream);
 }
 
 }  // namespace mask
@@ -341,18 +371,17 @@ extern "C" int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_
 }
 
 // transmitter [B, H, N, C] and receiver [B, H, C, N] statistics in one pass over attn [B, H, N, N]
-// (modeling_msvitencoder.py:182-190).  MSVIT_ERR_SHAPE for N beyond the register-resident row (N > 1024, or N > 256
-// when N is not a multiple of 4): those shapes take msvit_cluster_key_sums + msvit_pool.
+// (modeling_msvitencoder.py:182-190).  The one-pass kernel keeps a row and one accumulator per cluster in registers:
+// it is the faster route for N <= 256 and C <= 16 (measured, tools/microbench/next_rows_time.py) and returns
+// MSVIT_ERR_SHAPE beyond that, where msvit_cluster_key_sums + msvit_pool (two passes) win.
 extern "C" int msvit_cluster_attention_stats(const float* attn, const int64_t* cluster_indices, float* transmitter,
                                              float* receiver, int B, int H, int N, int C, msvit_stream_t stream_) {
   using namespace msvit;
   if (!attn || !cluster_indices || !transmitter || !receiver) return MSVIT_ERR_NULL;
-  if (B < 0 || H <= 0 || N <= 0 || C <= 0 || C > 64 || static_cast<long long>(B) * H > 65535) return MSVIT_ERR_SHAPE;
+  if (B < 0 || H <= 0 || N <= 0 || C <= 0 || C > 16 || N > 256 || static_cast<long long>(B) * H > 65535) return MSVIT_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(attn) & 15) != 0) return MSVIT_ERR_ALIGN;
-  const bool vec = (N & 3) == 0;
-  if (N > 32 * mask::kStatsChunks * (vec ? 4 : 1)) return MSVIT_ERR_SHAPE;
   if (B == 0) return MSVIT_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  return vec ? mask::dispatch_stats<4>(attn, cluster_indices, transmitter, receiver, B, H, N, C, stream)
-             : mask::dispatch_stats<1>(attn, cluster_indices, transmitter, receiver, B, H, N, C, stream);
+  if ((N & 3) == 0) return mask::dispatch_stats<4, 2>(attn, cluster_indices, transmitter, receiver, B, H, N, C, stream);
+  return mask::dispatch_stats<1, mask::kStatsChunks>(attn, cluster_indices, transmitter, receiver, B, H, N, C, stream);
 }

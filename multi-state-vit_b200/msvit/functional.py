@@ -403,8 +403,8 @@ def cluster_attention_stats(attention_probs: torch.Tensor, cluster_indices: torc
     with torch.cuda.device(a.device):
         tr = torch.empty(B, H, N, C, dtype=torch.float32, device=a.device)
         st = torch.cuda.current_stream(a.device).cuda_stream
-        if N <= (1024 if N % 4 == 0 else 256):
-            # one pass over the attention tensor for both statistics
+        if N <= 256 and C <= 16:
+            # one pass over the attention tensor for both statistics (the faster route in this range)
             rc = torch.empty(B, H, C, N, dtype=torch.float32, device=a.device)
             _lib.check(_lib.load().msvit_cluster_attention_stats(ops._ptr(a), ops._ptr(lab), ops._ptr(tr), ops._ptr(rc),
                                                                  B, H, N, C, st), "msvit_cluster_attention_stats")

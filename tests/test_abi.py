@@ -75,9 +75,10 @@ def test_argument_checks_fire_before_any_cuda_call(lib):
     assert lib.msvit_cluster_key_sums(p16 + 4, p16, p16, 1, 1, 8, 2, None) == -3
     assert lib.msvit_cluster_key_sums(p16, p16, p16, 0, 1, 8, 2, None) == 0
     assert lib.msvit_cluster_attention_stats(p16, p16, p16, None, 1, 1, 8, 2, None) == -1
-    assert lib.msvit_cluster_attention_stats(p16, p16, p16, p16, 1, 1, 2048, 2, None) == -2     # row beyond the registers
-    assert lib.msvit_cluster_attention_stats(p16, p16, p16, p16, 1, 1, 301, 2, None) == -2      # N % 4 != 0 and N > 256
+    assert lib.msvit_cluster_attention_stats(p16, p16, p16, p16, 1, 1, 2048, 2, None) == -2     # N > 256
+    assert lib.msvit_cluster_attention_stats(p16, p16, p16, p16, 1, 1, 301, 2, None) == -2      # N > 256
     assert lib.msvit_cluster_attention_stats(p16 + 4, p16, p16, p16, 1, 1, 8, 2, None) == -3
+    assert lib.msvit_cluster_attention_stats(p16, p16, p16, p16, 1, 1, 8, 17, None) == -2       # C > 16
     assert lib.msvit_cluster_attention_stats(p16, p16, p16, p16, 0, 1, 8, 2, None) == 0
     # empty batches are a no-op
     assert lib.msvit_affinity_degree(p16, 0, None, p16, 0, 0, 8, 8, 0, 3.0, 1.0, None, None, None) == 0

@@ -28,10 +28,12 @@ lab = torch.randint(0, C, (B, N), device=dev)
 ms = timeit(lambda: msvit.attention_mask(lab, max_n_clusters=C))
 L = 2 * C + N
 print(f"attention_mask B={B} N={N} C={C}: {ms:.4f} ms, {B * L * L / ms / 1e6:.0f} GB/s written")
-Bh, H = 128, 12
-attn = torch.softmax(torch.randn(Bh, H, N, N, device=dev), -1)
-labh = torch.randint(0, C, (Bh, N), device=dev)
-ms = timeit(lambda: msvit.cluster_attention_stats(attn, labh, C))
-byts = attn.numel() * 4
-print(f"cluster_attention_stats B={Bh} H={H} N={N} C={C}: {ms:.4f} ms for two passes over {byts / 1e6:.0f} MB of attention "
-      f"({2 * byts / ms / 1e6:.0f} GB/s)")
+for Bh, H, N, C in [(128, 12, 196, 8), (64, 12, 256, 16), (16, 12, 784, 39), (8, 12, 1100, 8)]:
+    attn = torch.softmax(torch.randn(Bh, H, N, N, device=dev), -1)
+    labh = torch.randint(0, C, (Bh, N), device=dev)
+    ms = timeit(lambda: msvit.cluster_attention_stats(attn, labh, C))
+    byts = attn.numel() * 4
+    route = "one pass" if N <= 256 and C <= 16 else "two passes"
+    print(f"cluster_attention_stats B={Bh} H={H} N={N} C={C}: {ms:.4f} ms, {byts / 1e6:.0f} MB of attention, {route} "
+          f"({byts / ms / 1e6:.0f} GB/s of attention per unit time)")
+    del attn
