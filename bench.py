@@ -110,8 +110,33 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None          # (module, handle) when NVML is importable: 2 ms cadence instead of nvidia-smi's 100 ms
+        self.samples = []
+        self.running = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1e3, int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -126,6 +151,19 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            sm = sorted(x[0] for x in self.samples)
+            bits = 0
+            for x in self.samples:
+                bits |= x[3]
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(max(x[1] for x in self.samples)),
+                    "reasons": sorted(nm for bit, nm in names.items() if bits & bit), "samples": len(sm),
+                    "power_w_max": round(max(x[2] for x in self.samples), 2), "source": "nvml, 2 ms cadence inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -352,6 +390,7 @@ def run_ours(args):
     barrier()
     e2e_wall = time.perf_counter() - wall0
     e2e_ms = reduce_max(max(e_begin.elapsed_time(e_end), 1e3 * e2e_wall))
+    h2d_bytes, d2h_bytes = hc.h2d_bytes, hc.d2h_bytes   # of the fp32 run (hc is rebuilt for the bf16 leg below)
     # the end-to-end results agree with the device-resident ones
     if not torch.equal(res.labels, out.labels.cpu()):
         raise RuntimeError("end-to-end labels differ from the device-resident run")
@@ -400,7 +439,6 @@ def run_ours(args):
 
     # ---- the other BASELINE.json configs as sub-records (C3, C4 with its three levels, C5 with its NCCL all-reduce)
     extras = {}
-    h2d_bytes, d2h_bytes = hc.h2d_bytes, hc.d2h_bytes
     if args.extras and args.config == "C2":
         del hc
         torch.cuda.empty_cache()
@@ -409,6 +447,11 @@ def run_ours(args):
                 extras[nm] = extra_per_image(nm, dev, world, rank, max(3, args.steps // 4), 3, barrier, reduce_max)
             except Exception as exc:  # a sub-record must not take the headline down
                 extras[nm] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            extras["C2_smooth_spectrum"] = smooth_spectrum_record(B, N, D, K, k, scale, dev, world, rank,
+                                                                  max(3, args.steps // 4), barrier, reduce_max)
+        except Exception as exc:
+            extras["C2_smooth_spectrum"] = {"error": f"{type(exc).__name__}: {exc}"}
         try:
             c5 = c5_measure(args, dev, world, rank, local, max(5, args.steps // 2), 3, with_e2e=False)
             if c5 is not None:
@@ -518,6 +561,35 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------ the other configs
+def smooth_spectrum_record(B, N, D, K, k, scale, dev, world, rank, steps, barrier, reduce_max):
+    """The C2 step on tokens WITHOUT planted clusters (msvit.synthetic.smooth_tokens: smooth random fields over the patch
+    grid, NCut eigenvalues decaying gradually): iteration counts and throughput where the solver has no spectral gap to
+    lean on.  Same kernels, same plan arguments as the headline."""
+    from msvit.functional import ClusterPlan
+    from msvit.synthetic import smooth_tokens
+    pool_n = 64
+    xs = smooth_tokens(pool_n, N, D, first=rank * pool_n)
+    x = xs.repeat((B + pool_n - 1) // pool_n, 1, 1)[:B].contiguous().to(dev)
+    plan = ClusterPlan(B, N, D, torch.float32, dev, ncut_dim=k, n_clusters=K, scale=scale)
+    for _ in range(3):
+        out = plan.run(x)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(steps):
+        out = plan.run(x)
+    t1.record()
+    barrier()
+    ms = reduce_max(t0.elapsed_time(t1)) / steps
+    it = out.iters.float()
+    return {"value": round(world * B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "scaling": "weak",
+            "workload": f"C2 shape [B={B} per GPU, N={N}, D={D}] float32, smooth-spectrum tokens (no planted clusters), "
+                        f"k={k} eigenvectors, K={K} k-means clusters, cluster-mean pooling",
+            "path": "fused (affinity in tensor memory)" if plan.fused else "affinity + eig kernels",
+            "eig_iters": {"mean": round(float(it.mean()), 2), "max": int(it.max())},
+            "converged_fraction": round(float(out.converged.float().mean()), 4)}
+
+
 def extra_per_image(name, dev, world, rank, steps, warmup, barrier, reduce_max):
     """C3 (ViT-L/14, 576 tokens, k=16) and C4 (1024 tokens, THREE hierarchical levels: 1 -> 4 -> 16 parents per image,
     every parent segment re-clustered into 4 children from that level's hidden states) as sub-records of the main

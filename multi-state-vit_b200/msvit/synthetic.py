@@ -87,6 +87,36 @@ def hierarchical_tokens(B: int, N: int, D: int, branch: int = 4, depth: int = 3,
     return x, leaf
 
 
+def smooth_tokens(B: int, N: int, D: int, n_freq: int = 64, alpha: float = 1.5, noise: float = 0.1, seed: int = 1212,
+                  first: int = 0) -> torch.Tensor:
+    """Tokens WITHOUT planted clusters: every feature channel is a random smooth field over the patch grid (2-D cosine
+    modes with power-law amplitudes (1 + u^2 + v^2)^(-alpha/2), unit variance per channel) plus white noise.  The NCut
+    spectrum of such an image decays gradually instead of showing a gap after K eigenvalues -- the hard case for a
+    subspace solver, used by bench.py to report iteration counts on non-planted data.  x [B, N, D] fp32."""
+    g = int(round(N ** 0.5))
+    if g * g == N:
+        ii = (torch.arange(g, dtype=torch.float64) + 0.5) / g
+        modes = [(u, v) for u in range(g) for v in range(g)]
+        modes.sort(key=lambda m: (m[0] ** 2 + m[1] ** 2, m))
+        modes = modes[1:n_freq + 1]                      # drop the constant mode
+        basis = torch.stack([(torch.cos(torch.pi * u * ii)[:, None] * torch.cos(torch.pi * v * ii)[None, :]).reshape(N)
+                             for u, v in modes], 1)      # [N, F]
+        amp = torch.tensor([(1.0 + u * u + v * v) ** (-alpha / 2) for u, v in modes], dtype=torch.float64)
+    else:
+        ii = (torch.arange(N, dtype=torch.float64) + 0.5) / N
+        freqs = torch.arange(1, n_freq + 1, dtype=torch.float64)
+        basis = torch.cos(torch.pi * freqs[None, :] * ii[:, None])
+        amp = (1.0 + freqs ** 2) ** (-alpha / 2)
+    basis = basis * amp[None, :]
+    basis = (basis / basis.pow(2).sum(1).mean().sqrt()).float()   # unit average variance per channel
+    x = torch.empty(B, N, D)
+    for i in range(B):
+        gen = torch.Generator().manual_seed(seed + 7919 * (first + i))
+        coef = torch.randn(basis.shape[1], D, generator=gen)
+        x[i] = basis @ coef + noise * torch.randn(N, D, generator=gen)
+    return x
+
+
 def planted_features(n: int, D: int, k: int, noise: float = 0.5, seed: int = 1212, first: int = 0,
                      chunk: int = 65536) -> torch.Tensor:
     """Rows first .. first+n-1 of the dataset-level (DeepCluster-style) workload: centres[lab] + noise."""
