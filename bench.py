@@ -110,7 +110,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
-        self.nvml = None          # (module, handle) when NVML is importable: 2 ms cadence instead of nvidia-smi's 100 ms
+        self.nvml = None          # (module, handle) when NVML is importable: sub-ms polling instead of nvidia-smi's 100 ms
         self.samples = []
         self.running = False
         try:
@@ -123,13 +123,20 @@ class ClockSampler:
     def _poll(self):
         nv, h = self.nvml
         reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        power, n = 0.0, 0
         while self.running:
             try:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetPowerUsage(h) / 1e3, int(reasons_fn(h))))
+                if n % 16 == 0:          # the power query is the slow one
+                    power = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, power, int(reasons_fn(h))))
             except Exception:
                 pass
-            time.sleep(0.002)
+            n += 1
+            time.sleep(0.0005)
 
     def start(self):
         if self.nvml is not None:
@@ -163,7 +170,7 @@ class ClockSampler:
             names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
             return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(max(x[1] for x in self.samples)),
                     "reasons": sorted(nm for bit, nm in names.items() if bits & bit), "samples": len(sm),
-                    "power_w_max": round(max(x[2] for x in self.samples), 2), "source": "nvml, 2 ms cadence inside the timed region"}
+                    "power_w_max": round(max(x[2] for x in self.samples), 2), "source": "nvml polled inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
