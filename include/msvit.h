@@ -158,7 +158,7 @@ int msvit_compose_labels(const int32_t* labels_sorted, const int32_t* n_child, c
  *   x [n, D] and centroids_op [k, D] share x_dtype (MSVIT_F32 is read as TF32, rounded to nearest);
  *   labels [n] int32; best [n] = the minimal score (may be NULL).  D*elsize % 16 == 0.
  * msvit_gkm_sort: stable counting sort of row ids by label: perm [n] (rows grouped by label, ascending row id
- *   inside a label), seg_off [k+1].  workspace: msvit_gkm_workspace_bytes(n, k) bytes.  k <= 12000.
+ *   inside a label), seg_off [k+1].  workspace: msvit_gkm_workspace_bytes(n, k) bytes.  k <= 10000.
  * msvit_gkm_accumulate: packed [k, D+1] fp32: columns [0, D) = sum of the member rows (fixed order, no atomics),
  *   column D = member count.  workspace (msvit_gkm_accumulate_workspace_bytes(k, D) bytes, may be NULL): partial sums
  *   of the runs every centroid's rows are cut into, so that very unequal clusters do not serialise on one CTA.

@@ -326,19 +326,25 @@ __global__ void __launch_bounds__(1024) label_scan_kernel(const int32_t* __restr
   if (threadIdx.x == 0) seg_off[k] = carry;
 }
 
-// perm[seg_off[c] + hist[b][c] + rank of the row among the block's rows with label c] = row   (one warp per block)
+// perm[seg_off[c] + hist[b][c] + rank of the row among the block's rows with label c] = row   (one warp per block).
+// The block's labels are fetched into shared memory in one go (all loads in flight together); the 64 ordered steps of
+// the stable placement then run at shared-memory latency instead of one global round trip each.
 __global__ void __launch_bounds__(32) scatter_kernel(const int32_t* __restrict__ labels, int n, int k,
                                                      const int32_t* __restrict__ hist,
                                                      const int32_t* __restrict__ seg_off, int32_t* __restrict__ perm) {
-  extern __shared__ int32_t cur[];
+  extern __shared__ int32_t cur[];          // [k] running output position per label, then [kSortRows] labels
+  int32_t* lab = cur + k;
   const int b = blockIdx.x, lane = threadIdx.x;
+  const int r0 = b * kSortRows, r1 = min(n, r0 + kSortRows);
+  for (int i = lane; i < r1 - r0; i += 32) {
+    const int c = labels[r0 + i];
+    lab[i] = (c < 0 || c >= k) ? -1 : c;
+  }
   for (int c = lane; c < k; c += 32) cur[c] = seg_off[c] + hist[static_cast<size_t>(b) * k + c];
   __syncwarp();
-  const int r0 = b * kSortRows, r1 = min(n, r0 + kSortRows);
   for (int base = r0; base < r1; base += 32) {
     const int r = base + lane;
-    int c = r < r1 ? labels[r] : -1;
-    if (c < 0 || c >= k) c = -1;
+    const int c = r < r1 ? lab[r - r0] : -1;
     const unsigned peers = __match_any_sync(0xffffffffu, c);
     const int rank = __popc(peers & ((1u << lane) - 1u));
     int pos = 0;
@@ -574,7 +580,7 @@ extern "C" int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* 
   using namespace msvit;
   using namespace msvit::gkm;
   if (!labels || !perm || !seg_off || !workspace) return MSVIT_ERR_NULL;
-  if (n < 0 || k <= 0 || n > 0x7fffff00LL || k > 12000) return MSVIT_ERR_SHAPE;  // k ints of counters live in shared memory
+  if (n < 0 || k <= 0 || n > 0x7fffff00LL || k > 10000) return MSVIT_ERR_SHAPE;  // k counters + one block of labels live in shared memory (48 KB)
   if (workspace_bytes < msvit_gkm_workspace_bytes(n, k)) return MSVIT_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int32_t* hist = static_cast<int32_t*>(workspace);
@@ -584,7 +590,8 @@ extern "C" int msvit_gkm_sort(const int32_t* labels, int64_t n, int k, int32_t* 
   int32_t* tot = hist + static_cast<size_t>(nb > 0 ? nb : 1) * k;
   block_offsets_kernel<<<ceil_div(k, 32), 32 * kOffWarps, 0, stream>>>(hist, nb, k, tot);
   label_scan_kernel<<<1, 1024, 0, stream>>>(tot, k, seg_off);
-  if (nb > 0) scatter_kernel<<<nb, 32, smem, stream>>>(labels, static_cast<int>(n), k, hist, seg_off, perm);
+  if (nb > 0)
+    scatter_kernel<<<nb, 32, smem + kSortRows * sizeof(int32_t), stream>>>(labels, static_cast<int>(n), k, hist, seg_off, perm);
   return cuda_status(cudaGetLastError());
 }
 
