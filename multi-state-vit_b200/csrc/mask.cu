@@ -157,6 +157,50 @@ __global__ void __launch_bounds__(256) key_sums_kernel(const float* __restrict__
 // size (receiver row).  Every attention element is loaded once: B*H*N*N*4 bytes read, (2 C / N) of that written.
 constexpr int kStatsChunks = 8;   // per-lane register chunks along the key axis: N <= 32 * 8 * VEC
 
+// Key sums for many clusters (C > 16): the predicated accumulators above cost C operations per attention element.
+// Here the image's keys are grouped by cluster once per CTA (stable, group_tokens); a warp stages one attention row in
+// shared memory (coalesced 128-bit loads) and lane c, c + 32, .. sums the row over the key list of its clusters in list
+// order -- N shared-memory reads per row whatever C is, fixed summation order (bit-reproducible).
+__global__ void __launch_bounds__(256) key_sums_sorted_kernel(const float* __restrict__ attn,
+                                                              const int64_t* __restrict__ cluster_indices,
+                                                              float* __restrict__ out, int H, int N, int C) {
+  extern __shared__ __align__(16) int sm[];
+  const int N4 = (N + 3) & ~3;
+  float* rows = reinterpret_cast<float*>(sm);                            // [warps][N4], 16-byte aligned rows
+  int* lab = sm + static_cast<size_t>(blockDim.x >> 5) * N4;             // [N4]
+  int* order = lab + N4;            // [N]   keys grouped by cluster
+  int* start = order + N;           // [C+1]
+  int* cursor = start + C + 1;      // [C]
+  const int bh = blockIdx.y, b = bh / H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  group_tokens(cluster_indices + static_cast<size_t>(b) * N, lab, order, start, cursor, N, C);
+  float* mine = rows + static_cast<size_t>(warp) * N4;
+  const bool vec = (N & 3) == 0;
+  for (int q = blockIdx.x * nwarps + warp; q < N; q += gridDim.x * nwarps) {
+    const float* row = attn + (static_cast<size_t>(bh) * N + q) * N;
+    if (vec) {
+      for (int k = 4 * lane; k < N; k += 128)
+        *reinterpret_cast<float4*>(mine + k) = __ldcs(reinterpret_cast<const float4*>(row + k));
+    } else {
+      for (int k = lane; k < N; k += 32) mine[k] = __ldcs(row + k);
+    }
+    __syncwarp();
+    float* o = out + (static_cast<size_t>(bh) * N + q) * C;
+    for (int c = lane; c < C; c += 32) {
+      const int s0 = start[c], s1 = start[c + 1];
+      float sum = 0.f;
+      int p = s0;
+      for (; p + 4 <= s1; p += 4) {
+        const float a0 = mine[order[p]], a1 = mine[order[p + 1]], a2 = mine[order[p + 2]], a3 = mine[order[p + 3]];
+        sum += a0; sum += a1; sum += a2; sum += a3;
+      }
+      for (; p < s1; ++p) sum += mine[order[p]];
+      o[c] = sum;
+    }
+    __syncwarp();
+  }
+}
+
 // Sum CMAX per-lane values over the warp with a transposing butterfly: at offsets 16, 8, ... a lane keeps one half of
 // its live values and hands the other half to its partner, so the 5 steps cost CMAX - 1 (+ the steps left once a
 // single value remains) shuffles instead of 5 CMAX.  On return acc[i], i < R, of lane l holds the total of column
@@ -365,8 +409,18 @@ extern "C" int msvit_cluster_key_sums(const float* attn, const int64_t* cluster_
   const size_t smem = static_cast<size_t>((N + 3) & ~3) * sizeof(int);
   if (C <= 8) mask::key_sums_kernel<8><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
   else if (C <= 16) mask::key_sums_kernel<16><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
-  else if (C <= 32) mask::key_sums_kernel<32><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
-  else mask::key_sums_kernel<64><<<grid, 256, smem, stream>>>(attn, cluster_indices, out, H, N, C);
+  else {
+    // one accumulator per cluster does not scale: keys grouped by cluster, rows staged in shared memory
+    const size_t N4 = static_cast<size_t>((N + 3) & ~3);
+    int warps = 8;
+    while (warps > 1 && warps * N4 * sizeof(float) > 40 * 1024) warps >>= 1;
+    const size_t smem2 = sizeof(int) * (N4 + N + 2 * static_cast<size_t>(C) + 1) + sizeof(float) * warps * N4;
+    cudaError_t e = cudaFuncSetAttribute(mask::key_sums_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem2));
+    if (e != cudaSuccess) return cuda_status(e);
+    const dim3 grid2((N + 8 * warps - 1) / (8 * warps), B * H);   // 8 rows per warp
+    mask::key_sums_sorted_kernel<<<grid2, 32 * warps, smem2, stream>>>(attn, cluster_indices, out, H, N, C);
+  }
   return cuda_status(cudaGetLastError());
 }
 
