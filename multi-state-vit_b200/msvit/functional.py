@@ -23,14 +23,45 @@ class ClusterOutput:
     labels: torch.Tensor            # [B, N] int64 child cluster ids (contiguous per image, ordered by parent)
     pooled: Optional[torch.Tensor]  # [B, K_pool, D] fp32 cluster means ("multi-state tokens")
     counts: Optional[torch.Tensor]  # [B, K_pool] int32
-    eigvecs: torch.Tensor           # [B, N, k] fp32, row i = embedding of token i inside its segment
     eigvals: torch.Tensor           # [B, P, k] fp32 (P parents per image)
     n_child: torch.Tensor           # [B, P] int32 children per parent
-    degree: torch.Tensor            # [B, N] fp32 NCut degree
     iters: torch.Tensor             # [B, P] int32 eigensolver iterations
     affinity: Optional[torch.Tensor] = None  # [B, N, N] fp32 (single-parent case with N % 4 == 0 only)
     verdict: Optional[torch.Tensor] = None   # [B, P] int32, fused path: 1 = the leading block met the tolerance
     iter_cap: int = 0                        # two-kernel path: the iteration cap (stopping there = not converged)
+    # eigenvectors / degrees as the kernels wrote them: token order for one parent, segment order (rows sorted by
+    # parent) otherwise -- then `perm` maps sorted row -> token row and `token_order` are the plan's [rows, k] / [rows]
+    # destination buffers.  The un-permutation runs when `eigvecs` / `degree` is first read, not in every step.
+    eigvecs_raw: Optional[torch.Tensor] = None
+    degree_raw: Optional[torch.Tensor] = None
+    perm: Optional[torch.Tensor] = None
+    token_order: Optional[tuple] = None
+    _unpermuted: bool = False
+
+    def _to_token_order(self):
+        if self.perm is not None and not self._unpermuted:
+            idx = self.perm.long()
+            self.token_order[0].index_copy_(0, idx, self.eigvecs_raw)
+            self.token_order[1].index_copy_(0, idx, self.degree_raw)
+            self._unpermuted = True
+
+    @property
+    def eigvecs(self) -> torch.Tensor:
+        """[B, N, k] fp32, row i = embedding of token i inside its segment."""
+        B, N = self.labels.shape
+        if self.perm is None:
+            return self.eigvecs_raw.view(B, N, -1)
+        self._to_token_order()
+        return self.token_order[0].view(B, N, -1)
+
+    @property
+    def degree(self) -> torch.Tensor:
+        """[B, N] fp32 NCut degree of every token inside its segment."""
+        B, N = self.labels.shape
+        if self.perm is None:
+            return self.degree_raw.view(B, N)
+        self._to_token_order()
+        return self.token_order[1].view(B, N)
 
     @property
     def converged(self) -> torch.Tensor:
@@ -258,20 +289,14 @@ class ClusterPlan:
                                      self.Kp, st), "msvit_pool")
             mark(6)
 
-        if self.perm is not None:
-            # eigenvectors / degree back in token order (plan-owned buffers: no allocation per run)
-            idx = self.perm.long()
-            self.V_tok.index_copy_(0, idx, self.V)
-            self.deg_tok.index_copy_(0, idx, self.deg)
-            V_tok, deg_tok = self.V_tok, self.deg_tok
-        else:
-            V_tok, deg_tok = self.V, self.deg
         aff = self.A.view(B, N, N) if (P == 1 and N % 4 == 0 and not self.fused) else None
         # the fused kernel reports its verdict; the two-kernel solver stops at the cap only when it did not converge
-        return ClusterOutput(labels=self.child, pooled=self.pooled, counts=self.counts, eigvecs=V_tok.view(B, N, k),
+        return ClusterOutput(labels=self.child, pooled=self.pooled, counts=self.counts,
                              eigvals=self.lam.view(B, P, k), n_child=self.n_child.view(B, P),
-                             degree=deg_tok.view(B, N), iters=self.iters.view(B, P), affinity=aff,
-                             verdict=self.info.view(B, P) if self.fused else None, iter_cap=self.eig_iters)
+                             iters=self.iters.view(B, P), affinity=aff,
+                             verdict=self.info.view(B, P) if self.fused else None, iter_cap=self.eig_iters,
+                             eigvecs_raw=self.V, degree_raw=self.deg, perm=self.perm,
+                             token_order=(self.V_tok, self.deg_tok) if self.perm is not None else None)
 
 
 def cluster_tokens(x: torch.Tensor, parent_indices: Optional[torch.Tensor] = None, *, ncut_dim: int,
