@@ -62,6 +62,7 @@ constexpr int kSliceBytes = 128;
 constexpr int kMaxStages = 6;
 constexpr int kTmemCols = 512;
 constexpr int kMB = 16;               // subspace block width (columns of U)
+static_assert(kCompute == kMB * kMB, "the Ritz rotation fills the kMB x kMB matrix with one entry per compute thread");
 constexpr int kMaxT = 208;            // 2 * 208 affinity columns + 96 accumulator columns fill the 512 of TMEM
 constexpr int kTileCols = 208;        // TMEM column stride of the two affinity tiles
 constexpr float kUScale = 1024.f;     // |u| <= 1 for a D-orthonormal block (deg >= 1): fp16 operands never overflow
