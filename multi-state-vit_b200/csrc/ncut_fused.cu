@@ -84,6 +84,7 @@ struct Params {
   int mode;
   float c2;
   int n_kslices, k_step, stages, stage_bytes, tail_rows;
+  float in_scale;   // fp16 Gram: the tokens are multiplied by this power of two before the conversion
   int m, kconv, max_iter, fast_iters;
   float tol, lam_floor;
   int debug;        // development: stop the segment early (0 = off)
@@ -169,7 +170,43 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 
-template <bool TF32>
+// Token input of the Gram contraction.
+//   kInBf16: bf16 tokens, kind::f16 straight from the TMA stages.
+//   kInTf32: fp32 tokens rounded to TF32 in place by the compute warps, kind::tf32 (any distance mode).
+//   kInFp16: fp32 tokens scaled by a power of two, rounded to the same 11-bit significand and converted IN PLACE to fp16
+//            by the compute warps (the 128-byte row of 32 fp32 becomes 64 bytes of fp16 in its first four 16-byte chunks);
+//            kind::f16 then needs half the instructions and reads half the bytes per k-slice.  rbf distance only: the
+//            caller's distance scale fixes the magnitude of the tokens that matter, which chooses the power of two.
+constexpr int kInBf16 = 0, kInTf32 = 1, kInFp16 = 2;
+
+// Row of an fp32 k-slice (128 bytes, 128B-swizzled by TMA; `row` = its index in the tile) -> fp16 in logical chunks 0..3
+// of the same row (round to nearest even, saturating; the token norms come from the diagonal of the Gram matrix, i.e.
+// from the converted values themselves).
+__device__ __forceinline__ void convert_row_fp16(uint8_t* rowp, int row, int lane, float scale) {
+  const int sw = row & 7;                      // physical 16-byte chunk = logical chunk ^ sw
+  uint4 q[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)                  // physical chunk (c + lane) & 7: the 8 lanes of a phase hit 8 bank groups
+    q[c] = *reinterpret_cast<const uint4*>(rowp + (((c + lane) & 7) << 4));
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    // the physical pair (pe, pe + 1), pe even: q[c] and q[c + 1] for an even lane, q[c - 1] and q[c] for an odd one
+    const int pe = (c + lane) & 6;
+    uint4 a4 = (lane & 1) ? q[(c + 7) & 7] : q[c];          // physical pe
+    uint4 b4 = (lane & 1) ? q[c] : q[c + 1];                // physical pe + 1
+    if (sw & 1) { const uint4 t = a4; a4 = b4; b4 = t; }    // logical order inside the pair
+    const uint32_t w[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+    uint32_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e])
+          : "f"(__uint_as_float(w[2 * e + 1]) * scale), "f"(__uint_as_float(w[2 * e]) * scale));
+    const int j = (pe ^ sw) >> 1;                            // logical pair = logical 16-byte chunk of the fp16 row
+    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+  }
+}
+
+template <int IN>
 __global__ void __launch_bounds__(kThreads, 1)
 ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_constant__ CUtensorMap tm_tail,
                   const Params P) {
@@ -177,6 +214,8 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
   // (pointer arithmetic on the shared array itself, not on an integer: the compiler keeps the shared address space and
   // emits LDS / STS instead of generic loads and stores for everything derived from it)
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr bool TF32 = IN == kInTf32;
+  constexpr bool CONV = IN != kInBf16;   // the compute warps rewrite the staged tile before the tensor core reads it
   uint8_t* uop = tiles + static_cast<size_t>(P.stages) * P.stage_bytes;   // 1024-aligned (stage_bytes % 1024 == 0)
   Shared& sh = *reinterpret_cast<Shared*>(uop + kUopBytes);
   float* ef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(&sh) + ((sizeof(Shared) + 15) & ~size_t(15)));
@@ -233,19 +272,20 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ Gram MMA issuer (lane 0 issues and commits)
-    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 128u, static_cast<uint32_t>(T));
+    const uint32_t idesc = make_idesc(TF32 ? 2u : (IN == kInFp16 ? 0u : 1u), 128u, static_cast<uint32_t>(T));
+    constexpr int kSteps = IN == kInFp16 ? 2 : 4;   // MMA k-steps per staged row: 64 bytes of fp16, else the whole 128 bytes
     for (int s = blockIdx.x; s < P.S; s += gridDim.x, ++job) {
       mbar_wait(&sh.tmem_empty, (job & 1) ^ 1);
       tc_fence_after();
       for (int ks = 0; ks < P.n_kslices; ++ks, ++it_ring) {
         const int st = it_ring % P.stages;
         const uint32_t ph = (it_ring / P.stages) & 1;
-        mbar_wait(TF32 ? &sh.conv[st] : &sh.full[st], ph);
+        mbar_wait(CONV ? &sh.conv[st] : &sh.full[st], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t b_addr = smem_u32(tiles + static_cast<size_t>(st) * P.stage_bytes);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 4 x 32 bytes of K per 128-byte slice
+          for (int kk = 0; kk < kSteps; ++kk) {  // 32 bytes of K per step
             const uint64_t bd = make_kmajor_sw128_desc(b_addr + kk * 32);
             const uint32_t acc = (ks | kk) != 0 ? 1u : 0u;
             umma_ss<TF32>(tmem_base, bd, bd, idesc, acc);
@@ -382,21 +422,50 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
         const uint32_t ph = (it_ring / P.stages) & 1;
         mbar_wait(&sh.full[st], ph);
         uint8_t* bt = tiles + static_cast<size_t>(st) * P.stage_bytes;
-        if (ct < T) ss += row_sumsq<TF32>(bt + ct * kSliceBytes, lane);
-        if constexpr (TF32) fence_proxy_async_smem();  // the rounded tile must be visible to the tensor core
+        if constexpr (IN == kInFp16) {
+          if (ct < T) convert_row_fp16(bt + ct * kSliceBytes, ct, lane, P.in_scale);
+        } else {
+          if (ct < T) ss += row_sumsq<TF32>(bt + ct * kSliceBytes, lane);
+        }
+        if constexpr (CONV) fence_proxy_async_smem();  // the rewritten tile must be visible to the tensor core
         __syncwarp();
         if (lane == 0) {
-          if constexpr (TF32) mbar_arrive(&sh.conv[st]);
+          if constexpr (CONV) mbar_arrive(&sh.conv[st]);
           mbar_arrive(&sh.empty[st]);
         }
       }
-      sh.rq[ct] = row_quantity(P.mode, ss, P.c2);
-      G::sync();
+      if constexpr (IN != kInFp16) {
+        sh.rq[ct] = row_quantity(P.mode, ss, P.c2);
+        G::sync();
+      }
 
       // ---- epilogue, in place in TMEM: 16 fp32 Gram columns -> 8 columns of fp16 pairs A_hi + 8 columns A_lo
       mbar_wait(&sh.tmem_full, job & 1);
       FPHASE_END(FP_GRAM);
       tc_fence_after();
+      if constexpr (IN == kInFp16) {
+        // fp16 Gram: the squared norm of a token is the diagonal of the Gram matrix (the same products, fp32
+        // accumulation), so the conversion loop above carries no per-element norm arithmetic.  A warp's 32 diagonal
+        // entries sit in two 16-column chunks of its own lanes.
+        const int rbase = tile * 128 + q * 32;
+        if (tile < n_tiles && rbase < T) {
+          float v0[16], v1[16];
+          tmem_ld16(lane_addr + a_col + rbase, v0);
+          if (rbase + 16 < T) tmem_ld16(lane_addr + a_col + rbase + 16, v1);
+          else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v1[e] = 0.f;
+          }
+          float g = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            g = lane == e ? v0[e] : g;
+            g = lane == 16 + e ? v1[e] : g;
+          }
+          sh.rq[row] = row_quantity(P.mode, g, P.c2);
+        }
+        G::sync();
+      }
       const float rq = sh.rq[row];
       float rowsum = 0.f;
       if (tile < n_tiles) {
@@ -801,6 +870,21 @@ extern "C" int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U
     P.debug = dbg ? atoi(dbg) : 0;
   }
 
+  // fp32 tokens under the rbf distance take the fp16 Gram: |xi - xj|^2 / scale is what the affinity depends on, so the
+  // tokens that matter have elements of the order sqrt(scale / D); they are multiplied by the power of two that brings
+  // that magnitude to about 16 (fp16 then spans 2^-18 .. 2^12 times it; larger elements saturate, which only happens for
+  // tokens whose affinity to everything else underflows anyway).  MSVIT_FUSED_TF32=1 keeps kind::tf32.
+  int in_mode = f32 ? kInTf32 : kInBf16;
+  P.in_scale = 1.0f;
+  if (f32 && mode == MSVIT_DIST_RBF && !getenv("MSVIT_FUSED_TF32")) {
+    const float mag = sqrtf(scale / static_cast<float>(D));
+    if (mag > 1e-30f && mag < 1e30f) {
+      in_mode = kInFp16;
+      P.in_scale = exp2f(rintf(log2f(16.0f / mag)));
+      P.c2 /= P.in_scale * P.in_scale;   // the Gram entries and the row norms carry in_scale^2
+    }
+  }
+
   const size_t fixed = 1024 + kUopBytes + ((sizeof(Shared) + 15) & ~size_t(15)) +
                        static_cast<size_t>(make_eig_layout().total) * sizeof(float);
   const size_t kMaxSmem = 227 * 1024;
@@ -818,14 +902,18 @@ extern "C" int msvit_ncut_fused(const void* x, int x_dtype, float* deg, float* U
 
   const int grid = S < sm_count() ? S : sm_count();
   cudaError_t e;
-  if (f32) {
-    e = cudaFuncSetAttribute(ncut_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (in_mode == kInFp16) {
+    e = cudaFuncSetAttribute(ncut_fused_kernel<kInFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_status(e);
-    ncut_fused_kernel<true><<<grid, kThreads, smem, stream>>>(tm_full, tm_tail, P);
+    ncut_fused_kernel<kInFp16><<<grid, kThreads, smem, stream>>>(tm_full, tm_tail, P);
+  } else if (in_mode == kInTf32) {
+    e = cudaFuncSetAttribute(ncut_fused_kernel<kInTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return cuda_status(e);
+    ncut_fused_kernel<kInTf32><<<grid, kThreads, smem, stream>>>(tm_full, tm_tail, P);
   } else {
-    e = cudaFuncSetAttribute(ncut_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = cudaFuncSetAttribute(ncut_fused_kernel<kInBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_status(e);
-    ncut_fused_kernel<false><<<grid, kThreads, smem, stream>>>(tm_full, tm_tail, P);
+    ncut_fused_kernel<kInBf16><<<grid, kThreads, smem, stream>>>(tm_full, tm_tail, P);
   }
   return cuda_status(cudaGetLastError());
 }

@@ -36,7 +36,10 @@ def test_fused_path_matches_two_kernel_path_and_oracle(dtype, shape):
     assert bool(fused.converged.all()) and bool(plain.converged.all())
     assert torch.equal(fused.labels, plain.labels)
     assert torch.equal(fused.counts, plain.counts)
-    torch.testing.assert_close(fused.degree, plain.degree, rtol=1e-5, atol=0)
+    # same arithmetic up to how an fp32 token is rounded to 11 significant bits on the way to the tensor core (fused:
+    # nearest-even fp16 conversion; two-kernel path: TF32 rounding, ties away) and to the summation order of the norms
+    # (two independent roundings of every token element, each within the stated bar of the exact value: the bar applies)
+    torch.testing.assert_close(fused.degree, plain.degree, rtol=RTOL if dtype == torch.float32 else 1e-5, atol=0)
     torch.testing.assert_close(fused.eigvals[:, 0, :K], plain.eigvals[:, 0, :K], rtol=1e-4, atol=1e-6)
     child, _, eigvals, _ = O.cluster_tokens(seen(x, dtype).double(), None, ncut_dim=K, n_clusters=K, scale=default_scale(D))
     assert torch.equal(fused.labels.cpu(), child)
