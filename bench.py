@@ -532,6 +532,9 @@ def run_ours(args):
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2_policy": f"inputs larger than L2 ({B * N * D * esz / 1e6:.0f} MB tokens per step vs 126 MB L2)",
                    "path": "fused (affinity in tensor memory)" if plan.fused else "affinity + eig kernels (affinity through L2)",
+                   "gram_operands": ("fp16, converted in place from the fp32 tokens: the 11-bit significand TF32 keeps; fp32 "
+                                     "accumulation, fp32 everywhere else" if (plan.fused and dtype == torch.float32)
+                                     else ("bf16 tokens" if dtype == torch.bfloat16 else "tf32")),
                    "eig_iters": eig_iters},
         "roofline": roof, "stages": stages,
         "cpu_baseline": {"value": round(cpu_rate, 2), "unit": UNIT, "cores": cores, "kind": "port",
