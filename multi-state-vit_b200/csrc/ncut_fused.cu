@@ -182,26 +182,26 @@ constexpr int kInBf16 = 0, kInTf32 = 1, kInFp16 = 2;
 // Row of an fp32 k-slice (128 bytes, 128B-swizzled by TMA; `row` = its index in the tile) -> fp16 in logical chunks 0..3
 // of the same row (round to nearest even, saturating; the token norms come from the diagonal of the Gram matrix, i.e.
 // from the converted values themselves).
-__device__ __forceinline__ void convert_row_fp16(uint8_t* rowp, int row, int lane, float scale) {
+__device__ __forceinline__ void convert_row_fp16(uint8_t* rowp, int row, float scale) {
   const int sw = row & 7;                      // physical 16-byte chunk = logical chunk ^ sw
+  const bool odd = (row & 1) != 0;
   uint4 q[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c)                  // physical chunk (c + lane) & 7: the 8 lanes of a phase hit 8 bank groups
-    q[c] = *reinterpret_cast<const uint4*>(rowp + (((c + lane) & 7) << 4));
+  for (int c = 0; c < 8; ++c)                  // physical chunk (c + row) & 7: 8 consecutive rows hit 8 bank groups
+    q[c] = *reinterpret_cast<const uint4*>(rowp + (((c + row) & 7) << 4));
 #pragma unroll
   for (int c = 0; c < 8; c += 2) {
-    // the physical pair (pe, pe + 1), pe even: q[c] and q[c + 1] for an even lane, q[c - 1] and q[c] for an odd one
-    const int pe = (c + lane) & 6;
-    uint4 a4 = (lane & 1) ? q[(c + 7) & 7] : q[c];          // physical pe
-    uint4 b4 = (lane & 1) ? q[c] : q[c + 1];                // physical pe + 1
-    if (sw & 1) { const uint4 t = a4; a4 = b4; b4 = t; }    // logical order inside the pair
+    // q[c] always holds the even logical chunk of its pair (physical (c + row) & 7, logical = physical ^ sw, and sw has
+    // the parity of row); its partner is the next physical chunk for an even row, the previous one for an odd row
+    const uint4 a4 = q[c];
+    const uint4 b4 = odd ? q[(c + 7) & 7] : q[c + 1];
     const uint32_t w[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
     uint32_t h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e])
           : "f"(__uint_as_float(w[2 * e + 1]) * scale), "f"(__uint_as_float(w[2 * e]) * scale));
-    const int j = (pe ^ sw) >> 1;                            // logical pair = logical 16-byte chunk of the fp16 row
+    const int j = ((((c + row) & 6)) ^ sw) >> 1;             // logical pair = logical 16-byte chunk of the fp16 row
     *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
   }
 }
@@ -423,7 +423,7 @@ ncut_fused_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_cons
         mbar_wait(&sh.full[st], ph);
         uint8_t* bt = tiles + static_cast<size_t>(st) * P.stage_bytes;
         if constexpr (IN == kInFp16) {
-          if (ct < T) convert_row_fp16(bt + ct * kSliceBytes, ct, lane, P.in_scale);
+          if (ct < T) convert_row_fp16(bt + ct * kSliceBytes, ct, P.in_scale);
         } else {
           if (ct < T) ss += row_sumsq<TF32>(bt + ct * kSliceBytes, lane);
         }
