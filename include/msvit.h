@@ -84,8 +84,12 @@ int msvit_ncut_eig(const float* A, const float* deg, float* V, float* lam, int32
                    int N, int k, int block, int max_iter, float tol, float lam_floor, int n_converge,
                    const int32_t* seg_off, const int64_t* a_off, msvit_stream_t stream);
 
-/* Fused affinity + NCut subspace iteration for whole images of N <= 224 tokens (uniform segments, N > block):
+/* Fused affinity + NCut subspace iteration for whole images of N <= 208 tokens (uniform segments, N > block):
  * the affinity is produced and consumed in tensor memory and never written to global memory.
+ * Operands of the Gram contraction: bf16 tokens as they are; fp32 tokens rounded to an 11-bit significand on the way to
+ * the tensor core -- under MSVIT_DIST_RBF as fp16 after a power-of-two scaling derived from `scale` (elements more than
+ * 2^12 times sqrt(scale / D) saturate: such a token is far from every other one either way), otherwise as TF32; fp32
+ * accumulation and fp32 arithmetic everywhere else.  The environment variable MSVIT_FUSED_TF32=1 forces TF32.
  * Replaces NCUT.fit_transform as msvit_affinity_degree + msvit_ncut_eig do (same call sites, sandbox/test.py:108-118);
  * the Rayleigh-Ritz rotation of the result is done by msvit_ritz_kmeans.
  * x [S*N, D] tokens (MSVIT_F32 | MSVIT_BF16), deg [S*N] NCut degree (out),
