@@ -71,7 +71,8 @@ def test_fused_threshold_mode_and_module_forward():
 
 def test_c1_error_against_the_unrounded_fp32_oracle():
     """BASELINE.json configs[0] (B=8): the whole path on fp32 tokens against the oracle fed the SAME un-rounded fp32
-    tokens (the tensor cores read them as TF32, so this includes the operand rounding): the stated bar is 1e-3."""
+    tokens (the tensor cores read them with an 11-bit significand -- fp16 after a power-of-two scaling in the fused kernel,
+    TF32 in the two-kernel path -- so this includes the operand rounding): the stated bar is 1e-3."""
     B, N, D, K = 8, 196, 768, 8
     x, _ = planted_tokens(B, N, D, K)
     xd = x.to(DEV)
