@@ -92,6 +92,26 @@ def test_c1_error_against_the_unrounded_fp32_oracle():
     assert all(v < RTOL for v in worst.values()), worst
 
 
+def test_fp16_gram_saturates_gracefully_on_outlier_elements():
+    """fp32 tokens go to the tensor core as fp16 after a power-of-two scaling; an element far outside that range
+    saturates.  Such a token is far from every other token with or without the saturation, so nothing else may move:
+    finite outputs, degree 1 for the outlier token (only its self-affinity survives), the other degrees as the oracle
+    computes them from the true values."""
+    B, N, D, K = 2, 196, 768, 8
+    x, _ = planted_tokens(B, N, D, K)
+    x[0, 5, 17] = 5.0e4          # 32 * 5e4 is beyond fp16
+    x[1, 100, 3] = -7.0e4
+    out = msvit.cluster_tokens(x.to(DEV), ncut_dim=K, n_clusters=K, scale=default_scale(D), fused=True)
+    for t in (out.degree, out.eigvals, out.eigvecs, out.pooled):
+        assert bool(torch.isfinite(t).all())
+    for b, i in ((0, 5), (1, 100)):
+        A = O.affinity(x[b].double(), "rbf", 3.0, default_scale(D))
+        deg = out.degree[b].cpu().double()
+        assert abs(float(deg[i]) - 1.0) < 1e-6
+        others = torch.arange(N) != i
+        np.testing.assert_allclose(deg[others].numpy(), A.sum(-1)[others].numpy(), rtol=RTOL)
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_degenerate_spectrum_iid_tokens(fused):
     """iid Gaussian tokens: lambda ~ [1, small, small, ...] with a slowly decaying noise bulk.
