@@ -371,11 +371,16 @@ def run_ours(args):
     barrier()
     t_begin.record()
     for s in range(args.steps):
-        out = plan.run(x, events=events[s])
+        out = plan.run(x)
     t_end.record()
     barrier()
     ms_total = reduce_max(t_begin.elapsed_time(t_end))
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel durations: the same K steps again with an event after every launch.  The events are kept out of the
+    # timed region above: seven records per step cost 18 us of the 0.5 ms step (tools/microbench/event_overhead.py)
+    for s in range(args.steps):
+        out = plan.run(x, events=events[s])
+    barrier()
     stage_ms = {name: sum(ev[i].elapsed_time(ev[i + 1]) for ev in events) / args.steps
                 for i, name in enumerate(ClusterPlan.STAGES)}
     iters = out.iters.float()
@@ -432,10 +437,13 @@ def run_ours(args):
         barrier()
         b0_.record()
         for s in range(args.steps):
-            out16 = plan16.run(x16, events=ev16[s])
+            out16 = plan16.run(x16)
         b1_.record()
         barrier()
         ms16d = reduce_max(b0_.elapsed_time(b1_)) / args.steps
+        for s in range(args.steps):
+            out16 = plan16.run(x16, events=ev16[s])
+        barrier()
         e2e_bf16["device_resident"] = {
             "value": round(world * B / ms16d * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms16d, 4),
             "stages_ms": {name: round(sum(ev[i].elapsed_time(ev[i + 1]) for ev in ev16) / args.steps, 4)
@@ -535,7 +543,9 @@ def run_ours(args):
                    "gram_operands": ("fp16, converted in place from the fp32 tokens: the 11-bit significand TF32 keeps; fp32 "
                                      "accumulation, fp32 everywhere else" if (plan.fused and dtype == torch.float32)
                                      else ("bf16 tokens" if dtype == torch.bfloat16 else "tf32")),
-                   "eig_iters": eig_iters},
+                   "eig_iters": eig_iters,
+                   "stage_timing": "`stages` / `roofline` come from a second pass of the same K steps with a CUDA event after "
+                                   "every launch; the timed region holds the launches only (the event records cost 18 us per step)"},
         "roofline": roof, "stages": stages,
         "cpu_baseline": {"value": round(cpu_rate, 2), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cpu_n} images of {args.config} in batches of 8 ({cpu_s:.1f} s), "
@@ -644,10 +654,13 @@ def extra_per_image(name, dev, world, rank, steps, warmup, barrier, reduce_max):
     barrier()
     t0.record()
     for s_ in range(steps):
-        outs = step(events[s_])
+        outs = step()
     t1.record()
     barrier()
     ms = reduce_max(t0.elapsed_time(t1)) / steps
+    for s_ in range(steps):          # per-kernel durations from a second, instrumented pass (see run_ours)
+        outs = step(events[s_])
+    barrier()
     stage_ms = {}
     for l in range(len(plans)):
         for i, nm in enumerate(ClusterPlan.STAGES):
