@@ -138,6 +138,19 @@ class ClockSampler:
             n += 1
             time.sleep(0.0005)
 
+    def sample_now(self):
+        """One sample taken by the calling thread (used after the last launch of the timed region has been enqueued,
+        while the GPU is still working through it)."""
+        if self.nvml is None or not self.running:
+            return
+        nv, h = self.nvml
+        try:
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                 nv.nvmlDeviceGetPowerUsage(h) / 1e3, int(reasons_fn(h))))
+        except Exception:
+            pass
+
     def start(self):
         if self.nvml is not None:
             self.running = True
@@ -373,6 +386,11 @@ def run_ours(args):
     for s in range(args.steps):
         out = plan.run(x)
     t_end.record()
+    # the launches are enqueued far ahead of the GPU: sample the clocks from this thread until the timed region has
+    # drained (an NVML query takes about a millisecond, so it must not sit between the launches)
+    if rank == 0:
+        while not t_end.query():
+            sampler.sample_now()
     barrier()
     ms_total = reduce_max(t_begin.elapsed_time(t_end))
     clocks = sampler.stop() if rank == 0 else None
